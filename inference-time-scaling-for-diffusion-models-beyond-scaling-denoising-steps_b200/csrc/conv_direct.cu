@@ -1,0 +1,255 @@
+// CUDA-core convolutions: the Cin=3 head and Cout=3 tail of the UNet (too thin
+// for a 128-wide tensor-core tile) and a plain reference implementation of the
+// tap-GEMM the tcgen05 kernel computes (debug twin + channel counts that are not
+// multiples of 64).
+#include "tapgemm.cuh"
+
+namespace its {
+
+// ---------------------------------------------------------------- head ----
+// out NHWC bf16 [n_img][H][W][Cout]; x NCHW fp32 [n_img_in][Cin][H][W];
+// W OIHW fp32 [Cout][Cin][3][3].  One thread = one pixel x 8 output channels.
+__global__ void __launch_bounds__(256) conv_head_kernel(
+    __nv_bfloat16* __restrict__ out, const float* __restrict__ x, const float* __restrict__ W,
+    const float* __restrict__ bias, int n_img, int n_img_in, int H, int Wd, int Cin, int Cout) {
+  extern __shared__ float s_w[];  // [Cin*9][Cout]
+  const int K = Cin * 9;
+  for (int i = threadIdx.x; i < K * Cout; i += blockDim.x) {
+    const int co = i / K, k = i - co * K;  // W[co][ci][ky][kx] flat = co*K + k
+    s_w[k * Cout + co] = W[i];
+  }
+  __syncthreads();
+  const int nv = Cout / 8;
+  const long long total = (long long)n_img * H * Wd * nv;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int cov = (int)(i % nv);
+    const long long pix = i / nv;
+    const int xw = (int)(pix % Wd);
+    const int y = (int)((pix / Wd) % H);
+    const int b = (int)(pix / ((long long)Wd * H));
+    const float* xin = x + (long long)(b % n_img_in) * Cin * H * Wd;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = bias ? bias[cov * 8 + j] : 0.f;
+    for (int ci = 0; ci < Cin; ++ci)
+      for (int ky = 0; ky < 3; ++ky) {
+        const int yy = y + ky - 1;
+        if (yy < 0 || yy >= H) continue;
+        for (int kx = 0; kx < 3; ++kx) {
+          const int xx = xw + kx - 1;
+          if (xx < 0 || xx >= Wd) continue;
+          const float v = __ldg(xin + ((long long)ci * H + yy) * Wd + xx);
+          const float* wr = s_w + ((ci * 3 + ky) * 3 + kx) * Cout + cov * 8;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] = fmaf(v, wr[j], acc[j]);
+        }
+      }
+    *reinterpret_cast<bf16x8*>(out + pix * Cout + cov * 8) = pack8(acc);
+  }
+}
+
+// ---------------------------------------------------------------- tail ----
+// act NHWC bf16 [n_img][H][W][Cin] (GroupNorm+Swish already applied);
+// out NCHW fp32 [n_img][Cout][H][W], Cout <= 4.  One warp per pixel.
+__global__ void __launch_bounds__(256) conv_tail_kernel(
+    float* __restrict__ out, const __nv_bfloat16* __restrict__ act, const float* __restrict__ W,
+    const float* __restrict__ bias, int n_img, int H, int Wd, int Cin, int Cout) {
+  extern __shared__ float s_w[];  // [9][Cin][4]
+  for (int i = threadIdx.x; i < 9 * Cin * 4; i += blockDim.x) {
+    const int co = i & 3, ci = (i >> 2) % Cin, tap = (i >> 2) / Cin;
+    s_w[i] = (co < Cout) ? W[((long long)co * Cin + ci) * 9 + tap] : 0.f;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int nv = Cin / 8;
+  const long long npix = (long long)n_img * H * Wd;
+  for (long long pix = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5; pix < npix;
+       pix += ((long long)gridDim.x * blockDim.x) >> 5) {
+    const int xw = (int)(pix % Wd);
+    const int y = (int)((pix / Wd) % H);
+    const long long b = pix / ((long long)Wd * H);
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    for (int e = lane; e < 9 * nv; e += 32) {
+      const int tap = e / nv, cv = e - tap * nv;
+      const int yy = y + tap / 3 - 1, xx = xw + tap % 3 - 1;
+      if (yy < 0 || yy >= H || xx < 0 || xx >= Wd) continue;
+      float f[8];
+      unpack8(*reinterpret_cast<const bf16x8*>(act + ((b * H + yy) * Wd + xx) * Cin + cv * 8), f);
+      const float4* wr = reinterpret_cast<const float4*>(s_w + ((long long)tap * Cin + cv * 8) * 4);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 wv = wr[j];
+        a0 = fmaf(f[j], wv.x, a0);
+        a1 = fmaf(f[j], wv.y, a1);
+        a2 = fmaf(f[j], wv.z, a2);
+        a3 = fmaf(f[j], wv.w, a3);
+      }
+    }
+    a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2); a3 = warp_sum(a3);
+    if (lane < Cout) {
+      const float v = (lane == 0 ? a0 : lane == 1 ? a1 : lane == 2 ? a2 : a3) + (bias ? bias[lane] : 0.f);
+      out[((b * Cout + lane) * H + y) * Wd + xw] = v;
+    }
+  }
+}
+
+// ------------------------------------------------- reference tap-GEMM ----
+// One thread per (GEMM row, output column); same parameter block, packed
+// weights and epilogue as the tcgen05 kernel.
+__global__ void __launch_bounds__(128) tapgemm_ref_kernel(const TapGemmParams p) {
+  const int n = blockIdx.y * blockDim.x + threadIdx.x;
+  const long long row = blockIdx.x;
+  const DevPhase& ph = p.phase[blockIdx.z];
+  if (n >= p.Cout) return;
+  const int x = (int)(row % p.Wm);
+  const int y = (int)((row / p.Wm) % p.Hm);
+  const int b = (int)(row / ((long long)p.Wm * p.Hm));
+  const __nv_bfloat16* wrow = p.w + (long long)b * p.w_batch_stride + (long long)n * p.w_pitch + ph.w_k0;
+  float acc = 0.f;
+  int k = 0;
+  for (int t = 0; t < ph.ntaps; ++t) {
+    const DevSrc& s = p.src[ph.src[t]];
+    const int yy = y * s.stride + ph.dy[t], xx = x * s.stride + ph.dx[t];
+    const bool inb = (yy >= 0 && yy < s.H && xx >= 0 && xx < s.W);
+    if (inb) {
+      const __nv_bfloat16* a =
+          s.ptr + (((long long)(s.bcast ? 0 : b) * s.H + yy) * s.W + xx) * s.c_pitch;
+      for (int c = 0; c < s.C; ++c)
+        acc = fmaf(__bfloat162float(a[c]), __bfloat162float(wrow[k + c]), acc);
+    }
+    k += s.C;
+  }
+  float v = acc * p.alpha;
+  if (p.bias) v += p.bias[n];
+  if (p.vec) v += p.vec[(long long)b * p.vec_stride + n];
+  if (p.vec2) v += p.vec2[(long long)b * p.vec2_stride + n];
+  const long long opix = ((long long)b * p.Hout + (y * p.out_scale + ph.py)) * p.Wout + (x * p.out_scale + ph.px);
+  if (p.res) v += __bfloat162float(p.res[opix * p.res_c_pitch + n]);
+  if (p.out_fp32)
+    static_cast<float*>(p.out)[opix * p.out_c_pitch + n] = v;
+  else
+    static_cast<__nv_bfloat16*>(p.out)[opix * p.out_c_pitch + n] = __float2bfloat16_rn(v);
+}
+
+int tapgemm_launch_ref(const TapGemmParams& p, cudaStream_t stream) {
+  const long long rows = (long long)p.B * p.Hm * p.Wm;
+  ITS_REQUIRE(rows <= 2147483647LL, "tapgemm_ref: too many rows");
+  dim3 grid((unsigned)rows, (p.Cout + 127) / 128, p.nphases);
+  tapgemm_ref_kernel<<<grid, 128, 0, stream>>>(p);
+  ITS_CHECK_LAUNCH();
+  return ITS_OK;
+}
+
+int tapgemm_build_params(const its_conv_desc* d, TapGemmParams* p, bool need_k64) {
+  ITS_REQUIRE(d != nullptr, "its_conv_igemm: null descriptor");
+  ITS_REQUIRE(d->nsrc >= 1 && d->nsrc <= ITS_MAX_SRC, "its_conv_igemm: nsrc=%d", d->nsrc);
+  ITS_REQUIRE(d->nphases >= 1 && d->nphases <= ITS_MAX_PHASES, "its_conv_igemm: nphases=%d", d->nphases);
+  ITS_REQUIRE(d->B > 0 && d->Hm > 0 && d->Wm > 0 && d->Cout > 0, "its_conv_igemm: bad B/Hm/Wm/Cout");
+  ITS_REQUIRE(d->w && d->out, "its_conv_igemm: null weight/out pointer");
+  ITS_REQUIRE(d->out_scale == 1 || d->out_scale == 2, "its_conv_igemm: out_scale=%d", d->out_scale);
+  ITS_REQUIRE(d->Hout == d->Hm * d->out_scale && d->Wout == d->Wm * d->out_scale,
+              "its_conv_igemm: Hout/Wout must equal Hm/Wm * out_scale");
+  memset(p, 0, sizeof(*p));
+  p->nsrc = d->nsrc;
+  p->nphases = d->nphases;
+  for (int s = 0; s < d->nsrc; ++s) {
+    const its_src_t& in = d->src[s];
+    ITS_REQUIRE(in.ptr && in.C > 0 && in.c_pitch >= in.c_off + in.C, "its_conv_igemm: src %d channels", s);
+    ITS_REQUIRE(in.stride == 1 || in.stride == 2, "its_conv_igemm: src %d stride=%d", s, in.stride);
+    ITS_REQUIRE(in.c_pitch % 8 == 0 && in.c_off % 8 == 0, "its_conv_igemm: src %d channel pitch/offset must be multiples of 8", s);
+    if (need_k64) ITS_REQUIRE(in.C % 64 == 0, "its_conv_igemm: src %d C=%d not a multiple of 64 (use impl=1)", s, in.C);
+    DevSrc& o = p->src[s];
+    o.ptr = static_cast<const __nv_bfloat16*>(in.ptr) + in.c_off;
+    o.c_pitch = in.c_pitch; o.C = in.C; o.H = in.H; o.W = in.W; o.stride = in.stride; o.bcast = in.bcast;
+  }
+  for (int f = 0; f < d->nphases; ++f) {
+    const its_phase_t& in = d->phase[f];
+    ITS_REQUIRE(in.ntaps >= 1 && in.ntaps <= ITS_MAX_TAPS, "its_conv_igemm: phase %d ntaps=%d", f, in.ntaps);
+    DevPhase& o = p->phase[f];
+    o.ntaps = in.ntaps; o.w_k0 = in.w_k0; o.py = in.py; o.px = in.px;
+    ITS_REQUIRE(in.py >= 0 && in.py < d->out_scale && in.px >= 0 && in.px < d->out_scale, "its_conv_igemm: phase %d offset", f);
+    int k = 0;
+    for (int t = 0; t < in.ntaps; ++t) {
+      ITS_REQUIRE(in.src[t] >= 0 && in.src[t] < d->nsrc, "its_conv_igemm: phase %d tap %d src", f, t);
+      o.src[t] = in.src[t]; o.dy[t] = in.dy[t]; o.dx[t] = in.dx[t];
+      k += d->src[in.src[t]].C;
+    }
+    o.nkb = k / 64;
+    ITS_REQUIRE(in.w_k0 >= 0 && in.w_k0 + k <= d->w_pitch, "its_conv_igemm: phase %d K range [%d,%d) exceeds w_pitch=%d", f, in.w_k0, in.w_k0 + k, d->w_pitch);
+    if (need_k64) ITS_REQUIRE(in.w_k0 % 8 == 0, "its_conv_igemm: phase %d w_k0 alignment", f);
+  }
+  p->B = d->B; p->Hm = d->Hm; p->Wm = d->Wm;
+  p->w = static_cast<const __nv_bfloat16*>(d->w);
+  p->w_pitch = d->w_pitch; p->w_batch_stride = d->w_batch_stride; p->Cout = d->Cout;
+  ITS_REQUIRE(d->out_c_pitch >= d->out_c_off + d->Cout, "its_conv_igemm: out channel pitch");
+  p->out_fp32 = d->out_fp32;
+  p->out = d->out_fp32 ? static_cast<void*>(static_cast<float*>(d->out) + d->out_c_off)
+                       : static_cast<void*>(static_cast<__nv_bfloat16*>(d->out) + d->out_c_off);
+  p->Hout = d->Hout; p->Wout = d->Wout; p->out_scale = d->out_scale; p->out_c_pitch = d->out_c_pitch;
+  p->bias = d->bias;
+  p->vec = d->vec ? d->vec + d->vec_off : nullptr;
+  p->vec_stride = d->vec_stride;
+  p->vec2 = d->vec2 ? d->vec2 + d->vec2_off : nullptr;
+  p->vec2_stride = d->vec2_stride;
+  p->res = d->res ? static_cast<const __nv_bfloat16*>(d->res) + d->res_c_off : nullptr;
+  p->res_c_pitch = d->res_c_pitch;
+  p->alpha = d->alpha;
+  // M tiling (used by the tcgen05 kernel): box of 128 GEMM rows
+  int bw = d->Wm < 128 ? d->Wm : 128;
+  int bh = 128 / bw; if (bh > d->Hm) bh = d->Hm;
+  int bb = 128 / (bw * bh);
+  p->bw = bw; p->bh = bh; p->bb = bb;
+  p->tiles_x = (d->Wm + bw - 1) / bw;
+  p->tiles_y = (d->Hm + bh - 1) / bh;
+  p->tiles_b = (d->B + bb - 1) / bb;
+  return ITS_OK;
+}
+
+}  // namespace its
+
+extern "C" int its_conv_head(void* out, const float* x, const float* W, const float* bias,
+                             int32_t n_img, int32_t n_img_in, int32_t H, int32_t Wd, int32_t Cin,
+                             int32_t Cout, void* stream) {
+  using namespace its;
+  ITS_REQUIRE(out && x && W, "its_conv_head: null pointer");
+  ITS_REQUIRE(n_img > 0 && n_img_in > 0 && H > 0 && Wd > 0 && Cin > 0 && Cin <= 4 && Cout % 8 == 0 && Cout > 0,
+              "its_conv_head: unsupported shape Cin=%d Cout=%d", Cin, Cout);
+  const size_t smem = (size_t)Cin * 9 * Cout * sizeof(float);
+  ITS_REQUIRE(smem <= 48 * 1024, "its_conv_head: Cout=%d too large", Cout);
+  const long long total = (long long)n_img * H * Wd * (Cout / 8);
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  conv_head_kernel<<<(unsigned)blocks, 256, smem, as_stream(stream)>>>(
+      static_cast<__nv_bfloat16*>(out), x, W, bias, n_img, n_img_in, H, Wd, Cin, Cout);
+  ITS_CHECK_LAUNCH();
+  return ITS_OK;
+}
+
+extern "C" int its_conv_tail(float* out, const void* act, const float* W, const float* bias,
+                             int32_t n_img, int32_t H, int32_t Wd, int32_t Cin, int32_t Cout,
+                             void* stream) {
+  using namespace its;
+  ITS_REQUIRE(out && act && W, "its_conv_tail: null pointer");
+  ITS_REQUIRE(n_img > 0 && H > 0 && Wd > 0 && Cin % 8 == 0 && Cin > 0 && Cout >= 1 && Cout <= 4,
+              "its_conv_tail: unsupported shape Cin=%d Cout=%d", Cin, Cout);
+  const size_t smem = (size_t)9 * Cin * 4 * sizeof(float);
+  ITS_REQUIRE(smem <= 48 * 1024, "its_conv_tail: Cin=%d too large", Cin);
+  const long long npix = (long long)n_img * H * Wd;
+  long long blocks = (npix * 32 + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  conv_tail_kernel<<<(unsigned)blocks, 256, smem, as_stream(stream)>>>(
+      out, static_cast<const __nv_bfloat16*>(act), W, bias, n_img, H, Wd, Cin, Cout);
+  ITS_CHECK_LAUNCH();
+  return ITS_OK;
+}
+
+extern "C" int its_conv_igemm(const its_conv_desc* desc_host, int32_t impl, void* stream) {
+  using namespace its;
+  TapGemmParams p;
+  int rc = tapgemm_build_params(desc_host, &p, impl == 0);
+  if (rc != ITS_OK) return rc;
+  if (impl == 1) return tapgemm_launch_ref(p, as_stream(stream));
+  ITS_REQUIRE(impl == 0, "its_conv_igemm: impl=%d", impl);
+  return tapgemm_launch_sm100(desc_host, p, as_stream(stream));
+}

@@ -1,0 +1,408 @@
+// Implicit-GEMM convolution ("tap-GEMM") on Blackwell tensor cores.
+//
+//   D[128 rows x BN cols] += A_tap[128 x 64] * W[BN x 64]^T     per k-block
+//
+// * GEMM rows are output pixels (b, y, x); a 128-row tile is a box of
+//   bb images x bh rows x bw columns of the NHWC bf16 activation tensor.  For
+//   each filter tap the A tile is that same box shifted by (dy, dx): a single
+//   4-D tiled TMA load (channels innermost, 64 channels = one 128-byte swizzle
+//   row per pixel).  Zero padding is TMA out-of-bounds fill, stride-2
+//   convolutions use the tensor map's element strides, nearest-upsample and
+//   transposed convolutions run as up to four sub-pixel phases (blockIdx.z) with
+//   their own tap tables and weight columns.
+// * Weights are a K-major bf16 matrix [Cout][K], loaded by a 3-D TMA (the third
+//   dimension is the per-image batch of the attention bmm's).
+// * tcgen05.mma (kind::f16, bf16 x bf16 -> fp32) is issued by one thread, the
+//   accumulator lives in TMEM; four epilogue warps read it back with tcgen05.ld
+//   and fuse alpha, bias, the per-image time/label-embedding vector, the
+//   residual, and the bf16 (or fp32) store.
+// * Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
+//   warps 2..5 = epilogue.  smem ring of STAGES {A 16 KB, B BN*128 B} buffers
+//   guarded by full/empty mbarriers; tcgen05.commit releases the slots.
+//
+// Reference semantics: see its_conv_igemm in include/its_b200.h.
+#include "tapgemm.cuh"
+#include <cuda.h>  // CUtensorMap (types only; the encoder is fetched at run time)
+
+namespace its {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int A_BYTES = BM * BK * 2;
+constexpr int NUM_THREADS = 192;
+constexpr uint32_t SPIN_LIMIT = 1u << 24;  // bounded waits: trap instead of hanging the GPU
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t ok = 0;
+#pragma unroll 1
+  for (uint32_t spin = 0; spin < SPIN_LIMIT; ++spin) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (ok) return;
+  }
+  __trap();  // a lost arrival would otherwise hang the device
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0,
+                                            int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1),
+        "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0,
+                                            int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1),
+        "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
+                                          uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                   smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),
+        "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]),
+        "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]),
+        "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 "version 1"):
+// rows of 128 bytes, 8-row swizzle atoms 1024 bytes apart.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFFu);       // start address, 16-byte units
+  d |= (uint64_t)1 << 16;                        // leading byte offset (ignored for SW128 K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;              // stride byte offset between 8-row groups
+  d |= (uint64_t)1 << 46;                        // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                        // layout type: SWIZZLE_128B
+  return d;
+}
+// Instruction descriptor: D fp32, A/B bf16, both K-major, M=128, N=BN.
+__host__ __device__ constexpr uint32_t make_idesc(int bn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+__host__ __device__ constexpr int tmem_cols_for(int bn) { return bn <= 32 ? 32 : bn <= 64 ? 64 : bn <= 128 ? 128 : 256; }
+
+template <int BN, int STAGES>
+struct SmemLayout {
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 1) * 8 + 8 + 1024;  // + alignment slack
+};
+
+template <int BN, int STAGES, int MIN_CTAS>
+__global__ void __launch_bounds__(NUM_THREADS, MIN_CTAS)
+tapgemm_sm100_kernel(const __grid_constant__ TapGemmParams p, const __grid_constant__ CUtensorMap tmA0,
+                     const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
+                     const __grid_constant__ CUtensorMap tmB) {
+  using L = SmemLayout<BN, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  // SWIZZLE_128B atoms need 1024-byte alignment in the shared address space
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const DevPhase& ph = p.phase[blockIdx.z];
+  const int nkb = ph.nkb;
+  const int mt = blockIdx.x;
+  const int tx = mt % p.tiles_x;
+  const int ty = (mt / p.tiles_x) % p.tiles_y;
+  const int tb = mt / (p.tiles_x * p.tiles_y);
+  const int n0 = blockIdx.y * BN;
+  constexpr int TMEM_COLS = tmem_cols_for(BN);
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(tmem_slot)),
+                 "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------ TMA producer ----
+    if (lane == 0) {
+      const int wb = (p.w_batch_stride != 0) ? tb * p.bb : 0;
+      int kb = 0;
+      for (int t = 0; t < ph.ntaps; ++t) {
+        const int si = ph.src[t];
+        const DevSrc& s = p.src[si];
+        const CUtensorMap* tm = (si == 0) ? &tmA0 : (si == 1) ? &tmA1 : &tmA2;
+        const int cx = tx * p.bw * s.stride + ph.dx[t];
+        const int cy = ty * p.bh * s.stride + ph.dy[t];
+        const int cb_img = s.bcast ? 0 : tb * p.bb;
+        const int ncb = s.C / BK;
+        for (int cb = 0; cb < ncb; ++cb, ++kb) {
+          const int stage = kb % STAGES;
+          const uint32_t parity = (uint32_t)((kb / STAGES) & 1);
+          mbar_wait(&empty_bar[stage], parity ^ 1u);
+          uint8_t* a_dst = smem + stage * L::STAGE_BYTES;
+          uint8_t* b_dst = a_dst + A_BYTES;
+          mbar_expect_tx(&full_bar[stage], (uint32_t)L::STAGE_BYTES);
+          tma_load_4d(a_dst, tm, &full_bar[stage], cb * BK, cx, cy, cb_img);
+          tma_load_3d(b_dst, &tmB, &full_bar[stage], ph.w_k0 + kb * BK, n0, wb);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------- MMA issuer -----
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BN);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int stage = kb % STAGES;
+        const uint32_t parity = (uint32_t)((kb / STAGES) & 1);
+        mbar_wait(&full_bar[stage], parity);
+        tcgen05_fence_after();
+        const uint32_t a_addr = smem_u32(smem + stage * L::STAGE_BYTES);
+        const uint64_t adesc = make_smem_desc(a_addr);
+        const uint64_t bdesc = make_smem_desc(a_addr + A_BYTES);
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k)
+          umma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (uint32_t)((kb | k) != 0));
+        umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+      }
+      umma_commit(tmem_full_bar);        // accumulator complete
+    }
+    __syncwarp();
+  } else {
+    // --------------------------------------------------- epilogue -----
+    const int q = warp & 3;              // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;
+    const int rb = row / (p.bh * p.bw);
+    const int ry = (row / p.bw) % p.bh;
+    const int rx = row % p.bw;
+    const int b = tb * p.bb + rb, y = ty * p.bh + ry, x = tx * p.bw + rx;
+    const bool valid = (b < p.B) && (y < p.Hm) && (x < p.Wm);
+    const long long opix =
+        ((long long)b * p.Hout + (y * p.out_scale + ph.py)) * p.Wout + (x * p.out_scale + ph.px);
+    const float* vec = p.vec ? p.vec + (long long)b * p.vec_stride : nullptr;
+    const float* vec2 = p.vec2 ? p.vec2 + (long long)b * p.vec2_stride : nullptr;
+    mbar_wait(tmem_full_bar, 0);
+    tcgen05_fence_after();
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+      if (valid) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const int n = n0 + c0 + g * 8;
+          if (n < p.Cout) {
+            float f[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[g * 8 + j]) * p.alpha;
+            if (p.bias) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) f[j] += __ldg(p.bias + n + j);
+            }
+            if (vec) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) f[j] += __ldg(vec + n + j);
+            }
+            if (vec2) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) f[j] += __ldg(vec2 + n + j);
+            }
+            if (p.res) {
+              float r[8];
+              unpack8(*reinterpret_cast<const bf16x8*>(p.res + opix * p.res_c_pitch + n), r);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) f[j] += r[j];
+            }
+            if (p.out_fp32) {
+              float4* dst = reinterpret_cast<float4*>(static_cast<float*>(p.out) + opix * p.out_c_pitch + n);
+              dst[0] = make_float4(f[0], f[1], f[2], f[3]);
+              dst[1] = make_float4(f[4], f[5], f[6], f[7]);
+            } else {
+              *reinterpret_cast<bf16x8*>(static_cast<__nv_bfloat16*>(p.out) + opix * p.out_c_pitch + n) =
+                  pack8(f);
+            }
+          }
+        }
+      }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+  }
+}
+
+// ---------------------------------------------------------------- host ----
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encoder() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(sym);
+  }
+  return fn;
+}
+
+static int encode_bf16_map(CUtensorMap* tm, int rank, const void* base, const cuuint64_t* dims,
+                           const cuuint64_t* strides_bytes, const cuuint32_t* box,
+                           const cuuint32_t* estr, const char* what) {
+  EncodeTiledFn enc = get_encoder();
+  ITS_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims,
+                   strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return set_error(ITS_ERR_CUDA,
+                     "cuTensorMapEncodeTiled(%s) failed: CUresult %d (rank %d dims %llu,%llu,%llu box %u,%u,%u)",
+                     what, (int)r, rank, (unsigned long long)dims[0], (unsigned long long)dims[1],
+                     (unsigned long long)dims[2], box[0], box[1], box[2]);
+  return ITS_OK;
+}
+
+template <int BN, int STAGES, int MIN_CTAS>
+static int launch_variant(const TapGemmParams& p, const CUtensorMap* tmA, const CUtensorMap& tmB,
+                          cudaStream_t stream) {
+  using L = SmemLayout<BN, STAGES>;
+  auto kern = tapgemm_sm100_kernel<BN, STAGES, MIN_CTAS>;
+  static bool configured = false;
+  if (!configured) {
+    ITS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    configured = true;
+  }
+  dim3 grid(p.tiles_x * p.tiles_y * p.tiles_b, (p.Cout + BN - 1) / BN, p.nphases);
+  kern<<<grid, NUM_THREADS, L::TOTAL, stream>>>(p, tmA[0], tmA[1], tmA[2], tmB);
+  ITS_CHECK_LAUNCH();
+  return ITS_OK;
+}
+
+int tapgemm_launch_sm100(const its_conv_desc* d, const TapGemmParams& p, cudaStream_t stream) {
+  // tile N
+  int bn = d->bn;
+  if (bn == 0) bn = (p.Cout % 256 == 0) ? 256 : (p.Cout % 192 == 0) ? 192 : (p.Cout % 128 == 0) ? 128 : 64;
+  ITS_REQUIRE(bn == 64 || bn == 128 || bn == 192 || bn == 256, "its_conv_igemm: bn=%d", bn);
+  ITS_REQUIRE(p.Cout % 8 == 0, "its_conv_igemm: Cout=%d must be a multiple of 8", p.Cout);
+  ITS_REQUIRE(p.Cout >= bn || p.Cout % 16 == 0, "its_conv_igemm: Cout=%d", p.Cout);
+  ITS_REQUIRE(p.w_pitch % 8 == 0 && p.w_batch_stride % 8 == 0, "its_conv_igemm: weight pitch alignment");
+  ITS_REQUIRE((reinterpret_cast<uintptr_t>(p.w) & 15) == 0, "its_conv_igemm: weight pointer alignment");
+  ITS_REQUIRE(p.bw * p.bh * p.bb == BM, "its_conv_igemm: Hm=%d Wm=%d do not tile into 128-row boxes", p.Hm, p.Wm);
+  ITS_REQUIRE(p.Wm % p.bw == 0 && p.Hm % p.bh == 0, "its_conv_igemm: Hm=%d Wm=%d not divisible by the tile box", p.Hm, p.Wm);
+  ITS_REQUIRE(p.w_batch_stride == 0 || p.bb == 1, "its_conv_igemm: per-image weights need Hm*Wm >= 128");
+  ITS_REQUIRE(p.out_c_pitch % 8 == 0 && (p.res == nullptr || p.res_c_pitch % 8 == 0), "its_conv_igemm: out/res pitch alignment");
+
+  CUtensorMap tmA[ITS_MAX_SRC];
+  memset(tmA, 0, sizeof(tmA));
+  for (int s = 0; s < p.nsrc; ++s) {
+    const DevSrc& in = p.src[s];
+    ITS_REQUIRE((reinterpret_cast<uintptr_t>(in.ptr) & 15) == 0, "its_conv_igemm: src %d pointer alignment", s);
+    ITS_REQUIRE(p.bw * in.stride <= 256 && p.bh * in.stride <= 256, "its_conv_igemm: box too large");
+    const cuuint64_t dims[4] = {(cuuint64_t)in.C, (cuuint64_t)in.W, (cuuint64_t)in.H,
+                                (cuuint64_t)(in.bcast ? 1 : p.B)};
+    const cuuint64_t strides[3] = {(cuuint64_t)in.c_pitch * 2, (cuuint64_t)in.W * in.c_pitch * 2,
+                                   (cuuint64_t)in.H * in.W * in.c_pitch * 2};
+    const cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)(p.bw * in.stride), (cuuint32_t)(p.bh * in.stride),
+                               (cuuint32_t)p.bb};
+    const cuuint32_t estr[4] = {1, (cuuint32_t)in.stride, (cuuint32_t)in.stride, 1};
+    int rc = encode_bf16_map(&tmA[s], 4, in.ptr, dims, strides, box, estr, "activations");
+    if (rc != ITS_OK) return rc;
+  }
+  for (int s = p.nsrc; s < ITS_MAX_SRC; ++s) tmA[s] = tmA[0];
+
+  int k_extent = 0;
+  for (int f = 0; f < p.nphases; ++f) {
+    const int k1 = p.phase[f].w_k0 + p.phase[f].nkb * BK;
+    if (k1 > k_extent) k_extent = k1;
+  }
+  CUtensorMap tmB;
+  {
+    const long long nbatch = (p.w_batch_stride != 0) ? p.B : 1;
+    const cuuint64_t dims[3] = {(cuuint64_t)k_extent, (cuuint64_t)p.Cout, (cuuint64_t)nbatch};
+    const cuuint64_t strides[2] = {(cuuint64_t)p.w_pitch * 2,
+                                   (cuuint64_t)((p.w_batch_stride != 0) ? p.w_batch_stride
+                                                                        : (long long)p.Cout * p.w_pitch) * 2};
+    const cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)bn, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    int rc = encode_bf16_map(&tmB, 3, p.w, dims, strides, box, estr, "weights");
+    if (rc != ITS_OK) return rc;
+  }
+  switch (bn) {
+    case 64:  return launch_variant<64, 4, 2>(p, tmA, tmB, stream);
+    case 128: return launch_variant<128, 3, 2>(p, tmA, tmB, stream);
+    case 192: return launch_variant<192, 5, 1>(p, tmA, tmB, stream);
+    default:  return launch_variant<256, 4, 1>(p, tmA, tmB, stream);
+  }
+}
+
+}  // namespace its

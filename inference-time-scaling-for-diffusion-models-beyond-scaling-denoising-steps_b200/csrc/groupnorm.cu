@@ -1,0 +1,157 @@
+// GroupNorm(32) [+ Swish] over NHWC bf16, with the skip-connection concat folded
+// in (two sources, one output).  HBM/L2-bound: one 16-byte load per 8 channels in
+// each of the two passes, one 16-byte store.  Deterministic (no float atomics):
+// pass 1 writes per-(image, chunk, group) partial sums, pass 2 reduces them in a
+// fixed order in double and applies scale/shift(+Swish).
+// Reference: nn.GroupNorm(32, C) + Swish at Model.py:170-173,186-190,132,257-259;
+// concat at Model.py:279-280.
+#include "its_common.cuh"
+
+namespace its {
+
+constexpr int GN_THREADS = 256;
+constexpr int GN_MAX_VEC = 128;  // C <= 1024
+
+struct GnArgs {
+  const __nv_bfloat16* src0;
+  const __nv_bfloat16* src1;
+  __nv_bfloat16* out;
+  const float* gamma;
+  const float* beta;
+  float* partials;
+  int C0, C1, C, HW, groups, chunks, silu;
+  float eps;
+};
+
+__device__ __forceinline__ bf16x8 gn_load(const GnArgs& a, long long pix, int c0) {
+  // pix = global pixel index (image*HW + p); c0 = first channel of the vector
+  if (c0 < a.C0)
+    return *reinterpret_cast<const bf16x8*>(a.src0 + pix * a.C0 + c0);
+  return *reinterpret_cast<const bf16x8*>(a.src1 + pix * a.C1 + (c0 - a.C0));
+}
+
+__global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(const GnArgs a) {
+  __shared__ float s_sum[GN_THREADS * 8];
+  __shared__ float s_sq[GN_THREADS * 8];
+  const int nvec = a.C / 8;
+  const int prow = GN_THREADS / nvec;  // pixel lanes per CTA (>= 2 for C <= 1024)
+  const int tid = threadIdx.x;
+  const int cv = tid % nvec, pl = tid / nvec;
+  const int chunk = blockIdx.x, img = blockIdx.y;
+  const int per = (a.HW + a.chunks - 1) / a.chunks;
+  const int p0 = chunk * per, p1 = min(a.HW, p0 + per);
+  float sum[8], sq[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) sum[i] = sq[i] = 0.f;
+  if (pl < prow) {
+    for (int p = p0 + pl; p < p1; p += prow) {
+      float f[8];
+      unpack8(gn_load(a, (long long)img * a.HW + p, cv * 8), f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { sum[i] += f[i]; sq[i] = fmaf(f[i], f[i], sq[i]); }
+    }
+    // layout [pl][channel]
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      s_sum[pl * a.C + cv * 8 + i] = sum[i];
+      s_sq[pl * a.C + cv * 8 + i] = sq[i];
+    }
+  }
+  __syncthreads();
+  // one warp per group (strided), fixed summation order -> deterministic
+  const int warp = tid >> 5, lane = tid & 31;
+  const int cg = a.C / a.groups;
+  for (int g = warp; g < a.groups; g += GN_THREADS / 32) {
+    float ps = 0.f, pq = 0.f;
+    const int n = cg * prow;
+    for (int e = lane; e < n; e += 32) {
+      const int r = e / cg, c = g * cg + (e - r * cg);
+      ps += s_sum[r * a.C + c];
+      pq += s_sq[r * a.C + c];
+    }
+    ps = warp_sum(ps);
+    pq = warp_sum(pq);
+    if (lane == 0) {
+      float* dst = a.partials + (((long long)img * a.chunks + chunk) * a.groups + g) * 2;
+      dst[0] = ps;
+      dst[1] = pq;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const GnArgs a) {
+  __shared__ float s_mean[64], s_rstd[64];
+  const int tid = threadIdx.x;
+  const int chunk = blockIdx.x, img = blockIdx.y;
+  const int cg = a.C / a.groups;
+  if (tid < a.groups) {
+    double s = 0.0, q = 0.0;
+    const float* src = a.partials + ((long long)img * a.chunks * a.groups + tid) * 2;
+    for (int c = 0; c < a.chunks; ++c) {
+      s += (double)src[(long long)c * a.groups * 2];
+      q += (double)src[(long long)c * a.groups * 2 + 1];
+    }
+    const double n = (double)cg * (double)a.HW;
+    const double mean = s / n;
+    double var = q / n - mean * mean;  // biased, like nn.GroupNorm
+    if (var < 0.0) var = 0.0;
+    s_mean[tid] = (float)mean;
+    s_rstd[tid] = (float)(1.0 / sqrt(var + (double)a.eps));
+  }
+  __syncthreads();
+  const int nvec = a.C / 8;
+  const int prow = GN_THREADS / nvec;
+  const int cv = tid % nvec, pl = tid / nvec;
+  if (pl >= prow) return;
+  float scale[8], shift[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = cv * 8 + i;
+    const int g = c / cg;
+    const float sc = s_rstd[g] * a.gamma[c];
+    scale[i] = sc;
+    shift[i] = a.beta[c] - s_mean[g] * sc;
+  }
+  const int per = (a.HW + a.chunks - 1) / a.chunks;
+  const int p0 = chunk * per, p1 = min(a.HW, p0 + per);
+  for (int p = p0 + pl; p < p1; p += prow) {
+    const long long pix = (long long)img * a.HW + p;
+    float f[8];
+    unpack8(gn_load(a, pix, cv * 8), f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float v = fmaf(f[i], scale[i], shift[i]);
+      f[i] = a.silu ? silu_f(v) : v;
+    }
+    *reinterpret_cast<bf16x8*>(a.out + pix * a.C + cv * 8) = pack8(f);
+  }
+}
+
+}  // namespace its
+
+extern "C" int its_group_norm(void* out, const void* src0, int32_t C0, const void* src1, int32_t C1,
+                              const float* gamma, const float* beta, int32_t n_img, int32_t HW,
+                              int32_t groups, float eps, int32_t silu, float* partials,
+                              int32_t chunks, void* stream) {
+  using namespace its;
+  ITS_REQUIRE(out && src0 && gamma && beta && partials, "its_group_norm: null pointer");
+  ITS_REQUIRE(C1 == 0 || src1 != nullptr, "its_group_norm: C1 > 0 needs src1");
+  const int C = C0 + C1;
+  ITS_REQUIRE(C0 > 0 && C0 % 8 == 0 && C1 % 8 == 0 && C <= 8 * GN_MAX_VEC,
+              "its_group_norm: channels (%d+%d) must be multiples of 8 and <= %d", C0, C1, 8 * GN_MAX_VEC);
+  ITS_REQUIRE(groups > 0 && groups <= 64 && C % groups == 0, "its_group_norm: C=%d not divisible by groups=%d", C, groups);
+  ITS_REQUIRE(n_img > 0 && HW > 0 && chunks > 0 && chunks <= HW, "its_group_norm: bad n_img/HW/chunks");
+  GnArgs a;
+  a.src0 = static_cast<const __nv_bfloat16*>(src0);
+  a.src1 = static_cast<const __nv_bfloat16*>(src1);
+  a.out = static_cast<__nv_bfloat16*>(out);
+  a.gamma = gamma; a.beta = beta; a.partials = partials;
+  a.C0 = C0; a.C1 = C1; a.C = C; a.HW = HW; a.groups = groups; a.chunks = chunks; a.silu = silu;
+  a.eps = eps;
+  dim3 grid(chunks, n_img);
+  gn_stats_kernel<<<grid, GN_THREADS, 0, as_stream(stream)>>>(a);
+  ITS_CHECK_LAUNCH();
+  gn_apply_kernel<<<grid, GN_THREADS, 0, as_stream(stream)>>>(a);
+  ITS_CHECK_LAUNCH();
+  return ITS_OK;
+}

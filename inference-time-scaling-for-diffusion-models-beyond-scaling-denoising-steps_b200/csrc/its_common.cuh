@@ -1,0 +1,101 @@
+// Shared helpers for libits_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include "../../include/its_b200.h"
+
+namespace its {
+
+// Per-thread error text returned by its_last_error_string().
+char* err_buf();
+int set_error(int code, const char* fmt, ...);
+
+#define ITS_CHECK_CUDA(expr)                                                   \
+  do {                                                                         \
+    cudaError_t _e = (expr);                                                   \
+    if (_e != cudaSuccess)                                                     \
+      return ::its::set_error(ITS_ERR_CUDA, "%s failed: %s (%s:%d)", #expr,    \
+                              cudaGetErrorString(_e), __FILE__, __LINE__);     \
+  } while (0)
+
+#define ITS_REQUIRE(cond, ...)                                                 \
+  do {                                                                         \
+    if (!(cond)) return ::its::set_error(ITS_ERR_INVALID, __VA_ARGS__);        \
+  } while (0)
+
+// Launch-error check that is safe under stream capture (no sync).
+#define ITS_CHECK_LAUNCH() ITS_CHECK_CUDA(cudaGetLastError())
+
+static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+__device__ __forceinline__ float silu_f(float v) { return v / (1.0f + __expf(-v)); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_min(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// 8 bf16 <-> 8 floats through one 16-byte access.
+struct alignas(16) bf16x8 { __nv_bfloat162 v[4]; };
+__device__ __forceinline__ void unpack8(const bf16x8& p, float* f) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 t = __bfloat1622float2(p.v[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ bf16x8 pack8(const float* f) {
+  bf16x8 p;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) p.v[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  return p;
+}
+
+// Philox4x32-10 (Salmon et al., SC'11), the counter-based generator the DDPM
+// step and the candidate generators share.  The host/oracle restatement is
+// oracle/philox.py.
+__host__ __device__ __forceinline__ void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint64_t p0 = (uint64_t)M0 * c[0];
+    uint64_t p1 = (uint64_t)M1 * c[2];
+    uint32_t hi0 = (uint32_t)(p0 >> 32), lo0 = (uint32_t)p0;
+    uint32_t hi1 = (uint32_t)(p1 >> 32), lo1 = (uint32_t)p1;
+    uint32_t n0 = hi1 ^ c[1] ^ k0;
+    uint32_t n2 = hi0 ^ c[3] ^ k1;
+    c[0] = n0; c[1] = lo1; c[2] = n2; c[3] = lo0;
+    k0 += W0; k1 += W1;
+  }
+}
+
+// Four N(0,1) draws for (seed, candidate, tag, quad index): Box-Muller on two
+// pairs of 32-bit uniforms mapped to (0,1].
+__device__ __forceinline__ void philox_normal4(uint64_t seed, uint64_t cand, uint32_t tag,
+                                               uint32_t quad, float z[4]) {
+  uint32_t c[4] = {quad, (uint32_t)cand, tag, (uint32_t)(cand >> 32)};
+  philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+  const float inv32 = 2.3283064365386963e-10f;  // 2^-32
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    float u1 = ((float)c[2 * i] + 1.0f) * inv32;      // (0,1]
+    float u2 = (float)c[2 * i + 1] * inv32;           // [0,1)
+    float r = sqrtf(-2.0f * __logf(u1));
+    float s, co;
+    __sincosf(6.283185307179586f * u2, &s, &co);
+    z[2 * i] = r * co;
+    z[2 * i + 1] = r * s;
+  }
+}
+
+}  // namespace its

@@ -1,0 +1,47 @@
+// Device-side parameter block shared by the tcgen05 tap-GEMM kernel
+// (conv_igemm_sm100.cu) and its CUDA-core reference twin (conv_direct.cu).
+#pragma once
+#include "its_common.cuh"
+
+namespace its {
+
+struct DevSrc {
+  const __nv_bfloat16* ptr;  // already offset by c_off
+  int c_pitch, C, H, W, stride, bcast;
+};
+
+struct DevPhase {
+  int ntaps, w_k0, py, px;
+  int nkb;                   // k-blocks of 64 in this phase
+  int8_t src[ITS_MAX_TAPS], dy[ITS_MAX_TAPS], dx[ITS_MAX_TAPS];
+};
+
+struct TapGemmParams {
+  DevSrc src[ITS_MAX_SRC];
+  DevPhase phase[ITS_MAX_PHASES];
+  int nsrc, nphases;
+  int B, Hm, Wm;
+  const __nv_bfloat16* w;
+  int w_pitch;
+  long long w_batch_stride;
+  int Cout;
+  void* out;                 // already offset by out_c_off
+  int out_fp32, Hout, Wout, out_scale, out_c_pitch;
+  const float* bias;
+  const float* vec;          // already offset by vec_off
+  int vec_stride;
+  const float* vec2;         // already offset by vec2_off
+  int vec2_stride;
+  const __nv_bfloat16* res;  // already offset by res_c_off
+  int res_c_pitch;
+  float alpha;
+  // M tiling: a 128-row tile is a (bb images) x (bh rows) x (bw cols) box
+  int bw, bh, bb, tiles_x, tiles_y, tiles_b;
+};
+
+// Validates the host descriptor and fills the device parameter block.
+int tapgemm_build_params(const its_conv_desc* d, TapGemmParams* p, bool need_k64);
+int tapgemm_launch_ref(const TapGemmParams& p, cudaStream_t stream);
+int tapgemm_launch_sm100(const its_conv_desc* d, const TapGemmParams& p, cudaStream_t stream);
+
+}  // namespace its
