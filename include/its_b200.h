@@ -215,7 +215,7 @@ int its_attention_small(void* out, const void* qkv, int32_t n_img, int32_t N,
  * Verifiers and selection.
  *   its_image_stats: per image mean, unbiased variance, min and the L2-
  *     normalised 8x8 average-pooled feature vector (verifier.py:62, 218-221,
- *     226, 277-284).  images NCHW fp32; stats [n_img][4] = {mean,var,min,0};
+ *     226, 277-284).  images NCHW fp32; stats [n_img][4] = {mean,var,min,|pooled|};
  *     feats [n_img][C*64] or NULL.
  *   its_candidate_scores: one score per candidate of `per_cand` consecutive
  *     images.  kind 0: 1/(1+mean var) (OracleVerifier.score, verifier.py:62-63)

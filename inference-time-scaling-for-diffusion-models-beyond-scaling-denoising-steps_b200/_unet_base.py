@@ -1,0 +1,62 @@
+"""What the two UNet shells share: plan cache, forward through the kernel plan.
+
+The shells are torch.nn.Modules only so that parameters live under the
+reference's state-dict keys (load_state_dict of a reference checkpoint works
+unchanged, `module.`-stripped or not).  Their sub-modules are parameter
+containers: no torch op of theirs runs on the sampling path."""
+from __future__ import annotations
+
+from typing import Dict, Optional, Tuple
+
+import torch
+from torch import nn
+
+from .engine import UNetPlan
+
+
+class ParamOnly(nn.Module):
+    """A sub-block whose arithmetic lives in the fused plan of the owning UNet."""
+
+    def forward(self, *a, **k):  # pragma: no cover - guard
+        raise RuntimeError(f"{type(self).__name__} is evaluated inside UNet.forward's kernel plan; "
+                           "call the UNet, not the sub-module")
+
+
+class PlannedUNet(nn.Module):
+    is_conditional = False
+
+    def _init_plans(self):
+        self._plans: Dict[Tuple, UNetPlan] = {}
+        self.register_load_state_dict_post_hook(lambda module, keys: module.invalidate_plans())
+
+    def invalidate_plans(self) -> None:
+        """Drop packed weights / buffers (call after mutating parameters in place)."""
+        self._plans = {}
+
+    def _apply(self, fn, *a, **k):  # .to() / .cuda() move the parameters: repack lazily
+        self._plans = {}
+        return super()._apply(fn, *a, **k)
+
+    def plan(self, n_img: int, H: int, W: int, *, n_img_in: Optional[int] = None, uniform_t: bool = False,
+             impl: Optional[int] = None) -> UNetPlan:
+        key = (n_img, H, W, n_img_in or n_img, uniform_t, impl, self.head.weight.data_ptr())
+        p = self._plans.get(key)
+        if p is None:
+            p = UNetPlan(self, n_img, H, W, n_img_in=n_img_in, uniform_t=uniform_t, impl=impl)
+            self._plans[key] = p
+        return p
+
+    def _run(self, x: torch.Tensor, t: torch.Tensor, labels: Optional[torch.Tensor]) -> torch.Tensor:
+        if x.device.type != "cuda":
+            raise RuntimeError("its_b200 UNet runs on CUDA only (no CPU fallback)")
+        if x.dim() != 4 or x.shape[1] != 3:
+            raise ValueError(f"expected x of shape [B,3,H,W], got {tuple(x.shape)}")
+        B, _, H, W = x.shape
+        p = self.plan(B, H, W, impl=getattr(self, "impl", None))
+        with torch.no_grad():
+            p.x_in.copy_(x)
+            p.t_idx.copy_(t.reshape(-1).to(torch.int64))
+            if labels is not None:
+                p.labels.copy_(labels.reshape(-1).to(torch.int64))
+        p.run()
+        return p.eps.clone()

@@ -199,6 +199,12 @@ int tapgemm_build_params(const its_conv_desc* d, TapGemmParams* p, bool need_k64
   int bw = d->Wm < 128 ? d->Wm : 128;
   int bh = 128 / bw; if (bh > d->Hm) bh = d->Hm;
   int bb = 128 / (bw * bh);
+  if (d->w_batch_stride != 0 && bb > 1) {
+    // per-image B operand: a tile must not span images.  Let the box overhang the
+    // image instead (TMA zero-fills, the epilogue predicates the rows away).
+    bh = 128 / bw;
+    bb = 1;
+  }
   p->bw = bw; p->bh = bh; p->bb = bb;
   p->tiles_x = (d->Wm + bw - 1) / bw;
   p->tiles_y = (d->Hm + bh - 1) / bh;

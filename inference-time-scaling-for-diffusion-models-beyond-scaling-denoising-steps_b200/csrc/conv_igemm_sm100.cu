@@ -30,7 +30,7 @@ constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int A_BYTES = BM * BK * 2;
 constexpr int NUM_THREADS = 192;
-constexpr uint32_t SPIN_LIMIT = 1u << 24;  // bounded waits: trap instead of hanging the GPU
+constexpr uint32_t SPIN_LIMIT = 1u << 20;  // bounded waits: trap instead of hanging the GPU
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -358,8 +358,9 @@ int tapgemm_launch_sm100(const its_conv_desc* d, const TapGemmParams& p, cudaStr
   ITS_REQUIRE(p.w_pitch % 8 == 0 && p.w_batch_stride % 8 == 0, "its_conv_igemm: weight pitch alignment");
   ITS_REQUIRE((reinterpret_cast<uintptr_t>(p.w) & 15) == 0, "its_conv_igemm: weight pointer alignment");
   ITS_REQUIRE(p.bw * p.bh * p.bb == BM, "its_conv_igemm: Hm=%d Wm=%d do not tile into 128-row boxes", p.Hm, p.Wm);
-  ITS_REQUIRE(p.Wm % p.bw == 0 && p.Hm % p.bh == 0, "its_conv_igemm: Hm=%d Wm=%d not divisible by the tile box", p.Hm, p.Wm);
-  ITS_REQUIRE(p.w_batch_stride == 0 || p.bb == 1, "its_conv_igemm: per-image weights need Hm*Wm >= 128");
+  ITS_REQUIRE(p.Wm % p.bw == 0 && (p.Hm % p.bh == 0 || p.bh > p.Hm),
+              "its_conv_igemm: Hm=%d Wm=%d not divisible by the tile box", p.Hm, p.Wm);
+  ITS_REQUIRE(p.w_batch_stride == 0 || p.bb == 1, "its_conv_igemm: per-image weights with a multi-image tile");
   ITS_REQUIRE(p.out_c_pitch % 8 == 0 && (p.res == nullptr || p.res_c_pitch % 8 == 0), "its_conv_igemm: out/res pitch alignment");
 
   CUtensorMap tmA[ITS_MAX_SRC];

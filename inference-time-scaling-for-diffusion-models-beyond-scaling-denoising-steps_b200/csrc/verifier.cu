@@ -26,7 +26,7 @@ __device__ __forceinline__ float block_min(float v, float* s_red) {
   return t;
 }
 
-// One CTA per image.  stats[img] = {mean, unbiased var, min, 0};
+// One CTA per image.  stats[img] = {mean, unbiased var, min, |pooled|_2 (0 without feats)};
 // feats[img][C*64] = L2-normalised adaptive 8x8 average pool (may be NULL).
 __global__ void __launch_bounds__(256) image_stats_kernel(float* __restrict__ stats,
                                                           float* __restrict__ feats,
@@ -71,7 +71,8 @@ __global__ void __launch_bounds__(256) image_stats_kernel(float* __restrict__ st
     sq = fmaf(a, a, sq);
   }
   sq = block_sum(sq, s_red);
-  const float inv = 1.0f / fmaxf(sqrtf(sq), 1e-12f);  // F.normalize eps
+  if (tid == 0) stats[(long long)img * 4 + 3] = sqrtf(sq);  // norm of the pooled vector
+  const float inv = 1.0f / fmaxf(sqrtf(sq), 1e-12f);         // F.normalize eps
   for (int f = tid; f < nf; f += blockDim.x) feats[(long long)img * nf + f] = s_feat[f] * inv;
 }
 

@@ -1,0 +1,382 @@
+"""Execution plans: the UNet forward as a fixed list of libits_b200 kernel launches.
+
+A `UNetPlan` is built once per (model, batch, resolution).  It owns
+  * packed weights (bf16, K-major [Cout][taps*Cin], shortcut / dual-conv / sub-pixel
+    phases concatenated along K) rebuilt from the nn.Parameters of the shell
+    modules (which keep the reference's state-dict layout),
+  * every activation buffer (NHWC bf16; HBM is 180 GB, nothing is recycled inside
+    a step so that a step is a pure function of (x, t, labels)),
+  * the launch list.  All launches go to the caller's current stream, never
+    synchronise or allocate, so a whole sampler step is captured into one CUDA
+    graph and replayed T times with the step index living on the device.
+
+torch is used here for device memory and streams only; all arithmetic on the hot
+path is in the .so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import ConvDesc
+
+BF16 = torch.bfloat16
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def pack_conv_weight(w: torch.Tensor) -> torch.Tensor:
+    """OIHW -> [Cout][kh*kw*Cin], tap-major then channel (the tap-GEMM's K order)."""
+    return w.detach().float().permute(0, 2, 3, 1).reshape(w.shape[0], -1)
+
+
+def taps_square(k: int, src: int = 0) -> List[Tuple[int, int, int]]:
+    p = k // 2
+    return [(src, ky - p, kx - p) for ky in range(k) for kx in range(k)]
+
+
+class UNetPlan:
+    """Launch plan of one UNet evaluation for n_img images of H x W."""
+
+    def __init__(self, model, n_img: int, H: int, W: int, *, n_img_in: Optional[int] = None,
+                 uniform_t: bool = False, impl: Optional[int] = None):
+        _lib.require_cuda()
+        self.L = _lib.lib()
+        self.model = model
+        self.cond = bool(getattr(model, "is_conditional", False))
+        self.n_img, self.H, self.W = int(n_img), int(H), int(W)
+        self.n_img_in = int(n_img_in or n_img)
+        self.uniform_t = uniform_t
+        self.dev = model.head.weight.device
+        if self.dev.type != "cuda":
+            raise RuntimeError("its_b200 UNet must live on a CUDA device (no CPU fallback); call .cuda()")
+        self.impl_forced = impl
+        self.keep: List[torch.Tensor] = []      # everything the launches point into
+        self.descs: List[ConvDesc] = []
+        self.ops: List[Tuple] = []
+        self.n_launches = 0
+        self.flops = 0                           # algorithmic 2*MAC of the tensor-core GEMMs + linears
+        with torch.no_grad():
+            self._build()
+
+    @classmethod
+    def scratch(cls, device, n_img: int, impl: Optional[int] = None) -> "UNetPlan":
+        """A plan without a model: lets tests and micro-benchmarks append single
+        launches (conv / group_norm / linear) through the same descriptor builder."""
+        _lib.require_cuda()
+        self = cls.__new__(cls)
+        self.L = _lib.lib()
+        self.model, self.cond = None, False
+        self.n_img, self.H, self.W, self.n_img_in = int(n_img), 0, 0, int(n_img)
+        self.uniform_t, self.dev, self.impl_forced = False, torch.device(device), impl
+        self.keep, self.descs, self.ops = [], [], []
+        self.n_launches, self.flops = 0, 0
+        self.gn_partials, self.tproj, self.cproj = None, None, None
+        return self
+
+    # ------------------------------------------------------------ buffers --
+    def _new(self, shape: Sequence[int], dtype=BF16) -> torch.Tensor:
+        t = torch.empty(tuple(int(s) for s in shape), dtype=dtype, device=self.dev)
+        self.keep.append(t)
+        return t
+
+    def _hold(self, t: torch.Tensor, dtype=None) -> torch.Tensor:
+        t = t.detach().to(device=self.dev, dtype=dtype or t.dtype).contiguous()
+        self.keep.append(t)
+        return t
+
+    def _op(self, fn, *args, launches: int = 1):
+        self.ops.append((fn, args))
+        self.n_launches += launches
+
+    # --------------------------------------------------------- primitives --
+    def _impl_for(self, chans: Sequence[int], cout: int) -> int:
+        if self.impl_forced is not None:
+            return self.impl_forced
+        ok = all(c % 64 == 0 for c in chans) and cout % 8 == 0 and cout >= 16
+        return 0 if ok else 1
+
+    def conv(self, srcs, phases, Hm, Wm, w, cout, *, out=None, out_scale=1, bias=None, vec=None,
+             vec_off=0, vec2=None, vec2_off=0, res=None, alpha=1.0, out_fp32=False, w_batch_stride=0,
+             w_pitch=None, B=None, out_shape=None) -> torch.Tensor:
+        """Append one tap-GEMM launch.  srcs: list of (tensor NHWC, C_used, c_off, stride, bcast);
+        phases: list of (taps[(src,dy,dx)], w_k0, py, px)."""
+        B = self.n_img if B is None else B
+        d = ConvDesc()
+        d.nsrc = len(srcs)
+        for i, (t, c_used, c_off, stride, bcast) in enumerate(srcs):
+            s = d.src[i]
+            s.ptr, s.c_pitch, s.c_off, s.C = t.data_ptr(), t.shape[-1], c_off, c_used
+            s.H, s.W, s.stride, s.bcast = t.shape[1], t.shape[2], stride, int(bcast)
+        d.nphases = len(phases)
+        for i, (taps, w_k0, py, px) in enumerate(phases):
+            ph = d.phase[i]
+            ph.ntaps, ph.w_k0, ph.py, ph.px = len(taps), w_k0, py, px
+            for j, (si, dy, dx) in enumerate(taps):
+                ph.src[j], ph.dy[j], ph.dx[j] = si, dy, dx
+            self.flops += 2 * B * Hm * Wm * cout * sum(srcs[si][1] for si, _, _ in taps)
+        d.B, d.Hm, d.Wm = B, Hm, Wm
+        d.w, d.w_pitch, d.w_batch_stride, d.Cout = w.data_ptr(), (w_pitch or w.shape[-1]), w_batch_stride, cout
+        Hout, Wout = Hm * out_scale, Wm * out_scale
+        if out is None:
+            out = self._new(out_shape or (B, Hout, Wout, cout), torch.float32 if out_fp32 else BF16)
+        d.out, d.out_fp32 = out.data_ptr(), int(out_fp32)
+        d.Hout, d.Wout, d.out_scale, d.out_c_pitch, d.out_c_off = Hout, Wout, out_scale, out.shape[-1], 0
+        d.bias = _ptr(bias)
+        if vec is not None:
+            d.vec, d.vec_stride, d.vec_off = vec.data_ptr(), (0 if vec.shape[0] == 1 else vec.shape[1]), vec_off
+        if vec2 is not None:
+            d.vec2, d.vec2_stride, d.vec2_off = vec2.data_ptr(), (0 if vec2.shape[0] == 1 else vec2.shape[1]), vec2_off
+        if res is not None:
+            d.res, d.res_c_pitch, d.res_c_off = res.data_ptr(), res.shape[-1], 0
+        d.alpha, d.bn = alpha, 0
+        impl = self._impl_for([s[1] for s in srcs], cout)
+        self.descs.append(d)
+        self._op(self.L.its_conv_igemm, C.byref(d), impl)
+        return out
+
+    def group_norm(self, srcs: Sequence[torch.Tensor], gn, silu: bool) -> torch.Tensor:
+        x0 = srcs[0]
+        x1 = srcs[1] if len(srcs) > 1 else None
+        B, H, W, C0 = x0.shape
+        C1 = x1.shape[-1] if x1 is not None else 0
+        Ct = C0 + C1
+        out = self._new((B, H, W, Ct))
+        HW = H * W
+        prow = max(1, 256 // (Ct // 8))
+        # the split depends on (HW, C) only, never on the batch: a candidate's numbers are then
+        # bit-identical whatever batch / rank it is evaluated in (fixed summation order)
+        chunks = max(1, min(HW // prow, 8))
+        need = B * chunks * 32 * 2
+        if self.gn_partials is None or self.gn_partials.numel() < need:
+            self.gn_partials = self._new((need,), torch.float32)
+        gamma, beta = self._hold(gn.weight, torch.float32), self._hold(gn.bias, torch.float32)
+        self._op(self.L.its_group_norm, out.data_ptr(), x0.data_ptr(), C0, _ptr(x1), C1, gamma.data_ptr(),
+                 beta.data_ptr(), B, HW, gn.num_groups, float(gn.eps), int(silu),
+                 self.gn_partials.data_ptr(), chunks, launches=2)
+        return out
+
+    def linear(self, x: torch.Tensor, W: torch.Tensor, b: Optional[torch.Tensor], *, silu_in=False,
+               silu_out=False) -> torch.Tensor:
+        rows, K = x.shape
+        N = W.shape[0]
+        y = self._new((rows, N), torch.float32)
+        self._op(self.L.its_linear, y.data_ptr(), x.data_ptr(), W.data_ptr(), _ptr(b), rows, K, N,
+                 int(silu_in), int(silu_out), 0)
+        self.flops += 2 * rows * K * N
+        return y
+
+    # ------------------------------------------------------------- blocks --
+    def _res_block(self, rb, xs: List[torch.Tensor], proj_off: int) -> torch.Tensor:
+        B, H, W = xs[0].shape[:3]
+        cin = sum(t.shape[-1] for t in xs)
+        cout = rb.block1[2].out_channels
+        a1 = self.group_norm(xs, rb.block1[0], silu=True)
+        w1 = self._hold(pack_conv_weight(rb.block1[2].weight), BF16)
+        b1 = self._hold(rb.block1[2].bias, torch.float32)
+        h1 = self.conv([(a1, cin, 0, 1, False)], [(taps_square(3), 0, 0, 0)], H, W, w1, cout, bias=b1,
+                       vec=self.tproj, vec_off=proj_off, vec2=self.cproj, vec2_off=proj_off)
+        a2 = self.group_norm([h1], rb.block2[0], silu=True)
+        conv2 = rb.block2[3]
+        w2 = pack_conv_weight(conv2.weight)
+        b2 = conv2.bias.detach().float()
+        has_sc = not isinstance(rb.shortcut, torch.nn.Identity)
+        if has_sc:
+            ws = rb.shortcut.weight.detach().float()[:, :, 0, 0]
+            w2 = self._hold(torch.cat([w2, ws], dim=1), BF16)
+            b2 = self._hold(b2 + rb.shortcut.bias.detach().float(), torch.float32)
+            srcs = [(a2, cout, 0, 1, False)] + [(t, t.shape[-1], 0, 1, False) for t in xs]
+            taps = taps_square(3) + [(1 + i, 0, 0) for i in range(len(xs))]
+            h2 = self.conv(srcs, [(taps, 0, 0, 0)], H, W, w2, cout, bias=b2)
+        else:
+            if len(xs) != 1:
+                raise RuntimeError("identity shortcut over a concatenated input is not supported")
+            w2 = self._hold(w2, BF16)
+            b2 = self._hold(b2, torch.float32)
+            h2 = self.conv([(a2, cout, 0, 1, False)], [(taps_square(3), 0, 0, 0)], H, W, w2, cout, bias=b2,
+                           res=xs[0])
+        if not isinstance(rb.attn, torch.nn.Identity):
+            h2 = self._attn_block(rb.attn, h2)
+        return h2
+
+    def _attn_block(self, at, x: torch.Tensor) -> torch.Tensor:
+        B, H, W, Cc = x.shape
+        N = H * W
+        scale = float(int(Cc) ** (-0.5))
+        a = self.group_norm([x], at.group_norm, silu=False)
+        wq, wk, wv = (m.weight.detach().float()[:, :, 0, 0] for m in (at.proj_q, at.proj_k, at.proj_v))
+        bq, bk, bv = (m.bias.detach().float() for m in (at.proj_q, at.proj_k, at.proj_v))
+        one = [(0, 0, 0)]
+        tensor_path = (N % 128 == 0) and self._impl_for([Cc, N], Cc) == 0
+        if tensor_path:
+            wqk = self._hold(torch.cat([wq, wk], 0), BF16)
+            bqk = self._hold(torch.cat([bq, bk], 0), torch.float32)
+            qk = self.conv([(a, Cc, 0, 1, False)], [(one, 0, 0, 0)], H, W, wqk, 2 * Cc, bias=bqk)
+            # V^T[b] = Wv . a[b]^T : weights are the A operand, the image is the B operand
+            wv_img = self._hold(wv.reshape(1, 1, Cc, Cc), BF16)
+            vT = self.conv([(wv_img, Cc, 0, 1, True)], [(one, 0, 0, 0)], 1, Cc, a.view(B, N, Cc), N,
+                           w_batch_stride=N * Cc, out_shape=(B, 1, Cc, N))
+            # S = scale * Q K^T (fp32), per image
+            k_view = qk.view(B, N, 2 * Cc)[:, :, Cc:]
+            S = self.conv([(qk, Cc, 0, 1, False)], [(one, 0, 0, 0)], H, W, k_view, N, alpha=scale,
+                          out_fp32=True, w_batch_stride=N * 2 * Cc, w_pitch=2 * Cc)
+            P = self._new((B, H, W, N))
+            self._op(self.L.its_softmax_rows, P.data_ptr(), S.data_ptr(), B * N, N)
+            bvh = self._hold(bv, torch.float32)
+            o = self.conv([(P, N, 0, 1, False)], [(one, 0, 0, 0)], H, W, vT.view(B, Cc, N), Cc, bias=bvh,
+                          w_batch_stride=Cc * N)
+        else:
+            if N > 64:
+                raise RuntimeError(f"attention with {N} tokens and {Cc} channels has no kernel "
+                                   "(needs C % 64 == 0 and N % 128 == 0, or N <= 64)")
+            wqkv = self._hold(torch.cat([wq, wk, wv], 0), BF16)
+            bqkv = self._hold(torch.cat([bq, bk, bv], 0), torch.float32)
+            qkv = self.conv([(a, Cc, 0, 1, False)], [(one, 0, 0, 0)], H, W, wqkv, 3 * Cc, bias=bqkv)
+            o = self._new((B, H, W, Cc))
+            self._op(self.L.its_attention_small, o.data_ptr(), qkv.data_ptr(), B, N, Cc, scale)
+            self.flops += 4 * B * N * N * Cc
+        wp = self._hold(at.proj.weight.detach().float()[:, :, 0, 0], BF16)
+        bp = self._hold(at.proj.bias, torch.float32)
+        return self.conv([(o, Cc, 0, 1, False)], [(one, 0, 0, 0)], H, W, wp, Cc, bias=bp, res=x)
+
+    def _down(self, ds, x: torch.Tensor) -> torch.Tensor:
+        B, H, W, Cc = x.shape
+        if hasattr(ds, "main"):       # Model.py:96-108
+            w = self._hold(pack_conv_weight(ds.main.weight), BF16)
+            b = self._hold(ds.main.bias, torch.float32)
+            taps = taps_square(3)
+        else:                          # ModelCondition.py:65-73: 3x3 s2 + 5x5 s2, one accumulator
+            w = self._hold(torch.cat([pack_conv_weight(ds.c1.weight), pack_conv_weight(ds.c2.weight)], 1), BF16)
+            b = self._hold(ds.c1.bias.detach().float() + ds.c2.bias.detach().float(), torch.float32)
+            taps = taps_square(3) + taps_square(5)
+        return self.conv([(x, Cc, 0, 2, False)], [(taps, 0, 0, 0)], H // 2, W // 2, w, Cc, bias=b)
+
+    def _up(self, us, x: torch.Tensor) -> torch.Tensor:
+        B, H, W, Cc = x.shape
+        if hasattr(us, "main"):
+            # nearest x2 + 3x3 (Model.py:122-125) folded into four 2x2 sub-pixel phases
+            w = us.main.weight.detach().float()
+            groups = {0: [(-1, [0]), (0, [1, 2])], 1: [(0, [0, 1]), (1, [2])]}
+            mats, phases, k0 = [], [], 0
+            for py in (0, 1):
+                for px in (0, 1):
+                    taps = []
+                    for dy, kys in groups[py]:
+                        for dx, kxs in groups[px]:
+                            mats.append(sum(w[:, :, ky, kx] for ky in kys for kx in kxs))
+                            taps.append((0, dy, dx))
+                    phases.append((taps, k0, py, px))
+                    k0 += len(taps) * Cc
+            wp = self._hold(torch.cat(mats, 1), BF16)
+            b = self._hold(us.main.bias, torch.float32)
+            return self.conv([(x, Cc, 0, 1, False)], phases, H, W, wp, Cc, out_scale=2, bias=b)
+        # ConvTranspose2d(5, 2, 2, 1) as four phases (ModelCondition.py:80), then 3x3
+        wt = us.t.weight.detach().float()  # [Cin, Cout, 5, 5]
+        mats, phases, k0 = [], [], 0
+        for py in (0, 1):
+            kys = [0, 2, 4] if py == 0 else [1, 3]
+            for px in (0, 1):
+                kxs = [0, 2, 4] if px == 0 else [1, 3]
+                taps = []
+                for ky in kys:
+                    for kx in kxs:
+                        mats.append(wt[:, :, ky, kx].t())
+                        taps.append((0, (py + 2 - ky) // 2, (px + 2 - kx) // 2))
+                phases.append((taps, k0, py, px))
+                k0 += len(taps) * Cc
+        wp = self._hold(torch.cat(mats, 1), BF16)
+        bt = self._hold(us.t.bias, torch.float32)
+        y = self.conv([(x, Cc, 0, 1, False)], phases, H, W, wp, Cc, out_scale=2, bias=bt)
+        wc = self._hold(pack_conv_weight(us.c.weight), BF16)
+        bc = self._hold(us.c.bias, torch.float32)
+        return self.conv([(y, Cc, 0, 1, False)], [(taps_square(3), 0, 0, 0)], 2 * H, 2 * W, wc, Cc, bias=bc)
+
+    # -------------------------------------------------------------- build --
+    def _build(self):
+        m, L = self.model, self.L
+        B, H, W = self.n_img, self.H, self.W
+        ch = m.head.out_channels
+        self.gn_partials = None
+        self.x_in = self._new((self.n_img_in, 3, H, W), torch.float32)
+        self.t_dev = torch.zeros(1, dtype=torch.int32, device=self.dev)
+        self.t_idx = torch.zeros(B, dtype=torch.int64, device=self.dev)
+        self.labels = torch.zeros(B, dtype=torch.int64, device=self.dev) if self.cond else None
+        rows = 1 if self.uniform_t else B
+        t_idx_ptr = None if self.uniform_t else self.t_idx.data_ptr()
+        te = m.time_embedding
+        emb = self._new((rows, ch), torch.float32)
+        if self.cond:
+            table = self._hold(te.timembedding[0].weight, torch.float32)
+            self._op(L.its_embed_rows, emb.data_ptr(), table.data_ptr(), t_idx_ptr, self.t_dev.data_ptr(), rows,
+                     ch, table.shape[0])
+            lin1, lin2 = te.timembedding[1], te.timembedding[3]
+        else:
+            freq = self._hold(te.freq_coeffs, torch.float32)
+            self._op(L.its_time_embed, emb.data_ptr(), t_idx_ptr, self.t_dev.data_ptr(), freq.data_ptr(), rows, ch)
+            lin1, lin2 = te.timembedding[0], te.timembedding[2]
+        hmid = self.linear(emb, self._hold(lin1.weight, torch.float32), self._hold(lin1.bias, torch.float32),
+                           silu_out=True)
+        temb = self.linear(hmid, self._hold(lin2.weight, torch.float32), self._hold(lin2.bias, torch.float32))
+        # every ResBlock's temb_proj (and cond_proj) as ONE linear over concatenated weights
+        blocks = [b for b in list(m.downblocks) + list(m.middleblocks) + list(m.upblocks) if hasattr(b, "temb_proj")]
+        offs, o = {}, 0
+        for rb in blocks:
+            offs[id(rb)] = o
+            o += rb.temb_proj[1].out_features
+        wt = self._hold(torch.cat([rb.temb_proj[1].weight.detach().float() for rb in blocks], 0), torch.float32)
+        bt = self._hold(torch.cat([rb.temb_proj[1].bias.detach().float() for rb in blocks], 0), torch.float32)
+        self.tproj = self.linear(temb, wt, bt, silu_in=True)
+        self.cproj = None
+        self._label_ops_start = None
+        if self.cond:
+            ce = m.cond_embedding.condEmbedding
+            ctab = self._hold(ce[0].weight, torch.float32)
+            cemb0 = self._new((B, ch), torch.float32)
+            self._op(L.its_embed_rows, cemb0.data_ptr(), ctab.data_ptr(), self.labels.data_ptr(), None, B, ch,
+                     ctab.shape[0])
+            c1 = self.linear(cemb0, self._hold(ce[1].weight, torch.float32), self._hold(ce[1].bias, torch.float32),
+                             silu_out=True)
+            cemb = self.linear(c1, self._hold(ce[3].weight, torch.float32), self._hold(ce[3].bias, torch.float32))
+            wc = self._hold(torch.cat([rb.cond_proj[1].weight.detach().float() for rb in blocks], 0), torch.float32)
+            bc = self._hold(torch.cat([rb.cond_proj[1].bias.detach().float() for rb in blocks], 0), torch.float32)
+            self.cproj = self.linear(cemb, wc, bc, silu_in=True)
+        # ---- head
+        h = self._new((B, H, W, ch))
+        hw, hb = self._hold(m.head.weight, torch.float32), self._hold(m.head.bias, torch.float32)
+        self._op(L.its_conv_head, h.data_ptr(), self.x_in.data_ptr(), hw.data_ptr(), hb.data_ptr(), B,
+                 self.n_img_in, H, W, 3, ch)
+        self.flops += 2 * B * H * W * ch * 27
+        hs = [h]
+        for layer in m.downblocks:
+            h = self._res_block(layer, [h], offs[id(layer)]) if hasattr(layer, "temb_proj") else self._down(layer, h)
+            hs.append(h)
+        for layer in m.middleblocks:
+            h = self._res_block(layer, [h], offs[id(layer)])
+        for layer in m.upblocks:
+            if hasattr(layer, "temb_proj"):
+                h = self._res_block(layer, [h, hs.pop()], offs[id(layer)])
+            else:
+                h = self._up(layer, h)
+        assert len(hs) == 0
+        a = self.group_norm([h], m.tail[0], silu=True)
+        self.eps = self._new((B, 3, H, W), torch.float32)
+        tw, tb = self._hold(m.tail[2].weight, torch.float32), self._hold(m.tail[2].bias, torch.float32)
+        self._op(L.its_conv_tail, self.eps.data_ptr(), a.data_ptr(), tw.data_ptr(), tb.data_ptr(), B, a.shape[1],
+                 a.shape[2], a.shape[3], 3)
+        self.flops += 2 * B * H * W * 3 * 9 * a.shape[3]
+
+    # ---------------------------------------------------------------- run --
+    def run(self) -> None:
+        """Enqueue every launch on the current stream (graph-capturable)."""
+        s = _lib.stream_ptr()
+        L = self.L
+        for fn, args in self.ops:
+            rc = fn(*args, s)
+            if rc != 0:
+                _lib.check(rc, fn.__name__)

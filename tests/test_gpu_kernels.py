@@ -1,0 +1,383 @@
+"""GPU: every kernel of libits_b200 against a plain torch fp32 statement of the same
+op (inputs/weights pre-rounded to bf16 where the kernel stores bf16), called
+through the C-ABI."""
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import ddpm_oracle as O
+from oracle import philox
+from tests import cases
+
+pytestmark = pytest.mark.gpu
+
+
+def bf(x):
+    return x.to(torch.bfloat16).to(torch.float32)
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _no_tf32():
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    yield
+
+
+def nhwc(x):  # NCHW fp32 -> NHWC bf16
+    return x.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
+
+
+def nchw(x):  # NHWC any -> NCHW fp32
+    return x.float().permute(0, 3, 1, 2).contiguous()
+
+
+def check_close(got, ref, tol, what=""):
+    """max |got-ref| <= tol * max|ref| (bf16 storage dominates the error budget)."""
+    err = (got - ref).abs().max().item()
+    scale = max(ref.abs().max().item(), 1e-6)
+    assert err <= tol * scale, f"{what}: max err {err:.4e} vs scale {scale:.4e} (tol {tol})"
+
+
+# ------------------------------------------------------------ DDPM step ------
+def _coef(T, dev):
+    from its_b200.Diffusion import GaussianDiffusionSampler
+    s = GaussianDiffusionSampler(torch.nn.Identity(), 1e-4, 0.02, T)
+    return s, s._coef_table(dev)
+
+
+@pytest.mark.parametrize("guided", [False, True])
+def test_ddpm_step_bit_exact_with_injected_noise(cuda_dev, built_lib, guided):
+    from its_b200 import _lib
+    T, B, n = 50, 5, 3 * 16 * 16
+    smp, coef = _coef(T, cuda_dev)
+    g = torch.Generator(device="cpu").manual_seed(3)
+    x = torch.randn(B, n, generator=g).to(cuda_dev)
+    e_c = torch.randn(B, n, generator=g).to(cuda_dev)
+    e_u = torch.randn(B, n, generator=g).to(cuda_dev) if guided else None
+    noise = torch.randn(T, B, n, generator=g).to(cuda_dev)
+    w = 1.8
+    for t in (T - 1, 7, 1, 0):
+        tt = torch.full((B,), t, dtype=torch.long, device=cuda_dev)
+        # reference expression order (Diffusion.py:67-72,99; DiffusionCondition.py:85)
+        eps = (1. + w) * e_c - w * e_u if guided else e_c
+        var = torch.cat([smp.posterior_var[1:2], smp.betas[1:]]).to(cuda_dev)
+        c1 = smp.coeff1.to(cuda_dev)[tt].float().view(B, 1)
+        c2 = smp.coeff2.to(cuda_dev)[tt].float().view(B, 1)
+        mean = c1 * x - c2 * eps
+        ref = mean + torch.sqrt(var[tt].float().view(B, 1)) * noise[t] if t > 0 else mean
+        ref_clip = torch.clip(ref, -1, 1) if t == 0 else ref
+        xk = x.clone()
+        t_dev = torch.tensor([t], dtype=torch.int32, device=cuda_dev)
+        flag = torch.zeros(1, dtype=torch.int32, device=cuda_dev)
+        _lib.check(built_lib.its_ddpm_step(xk.data_ptr(), e_c.data_ptr(), e_u.data_ptr() if guided else None,
+                                           noise.data_ptr(), B * n, B, n, coef.data_ptr(), t_dev.data_ptr(), w,
+                                           0, 0, flag.data_ptr(), 1, _lib.stream_ptr()))
+        torch.cuda.synchronize()
+        assert torch.equal(xk, ref_clip), f"t={t}: max diff {(xk - ref_clip).abs().max().item()}"
+        assert flag.item() == 0
+
+
+def test_ddpm_step_nan_flag_and_advance(cuda_dev, built_lib):
+    from its_b200 import _lib
+    _, coef = _coef(10, cuda_dev)
+    x = torch.zeros(2, 64, device=cuda_dev)
+    e = torch.zeros(2, 64, device=cuda_dev)
+    e[1, 5] = float("nan")
+    t_dev = torch.tensor([3], dtype=torch.int32, device=cuda_dev)
+    flag = torch.zeros(1, dtype=torch.int32, device=cuda_dev)
+    _lib.check(built_lib.its_ddpm_step(x.data_ptr(), e.data_ptr(), None, None, 0, 2, 64, coef.data_ptr(),
+                                       t_dev.data_ptr(), 0.0, 1, 0, flag.data_ptr(), 1, _lib.stream_ptr()))
+    _lib.check(built_lib.its_step_advance(t_dev.data_ptr(), -1, _lib.stream_ptr()))
+    assert flag.item() == 1 and t_dev.item() == 2
+
+
+def test_philox_matches_numpy_restatement(cuda_dev, built_lib):
+    from its_b200.search.search_algorithm import philox_normal
+    seed, cand0, tag = 0x1234567890ABCDEF & (2 ** 62 - 1), 5, 0x40000000
+    z = philox_normal((6, 3, 8, 8), seed, cand0, tag, cuda_dev).cpu().numpy().reshape(6, -1)
+    ref = philox.normal(seed, cand0, tag, 6, 192)
+    assert np.abs(z - ref).max() < 2e-4          # fast log / sincos intrinsics vs libm
+    base = torch.arange(192, dtype=torch.float32, device=cuda_dev)
+    z2 = philox_normal((6, 3, 8, 8), seed, cand0, tag, cuda_dev, base=base, scale=0.05).cpu().numpy().reshape(6, -1)
+    assert np.abs(z2 - (np.arange(192, dtype=np.float32)[None] + 0.05 * ref)).max() < 1e-4
+    big = philox_normal((64, 3, 32, 32), 99, 0, 7, cuda_dev)
+    assert abs(big.mean().item()) < 5e-3 and abs(big.std().item() - 1) < 5e-3
+    # a unit's stream depends on its global id only
+    part = philox_normal((2, 3, 32, 32), 99, 10, 7, cuda_dev)
+    assert torch.equal(part, big[10:12])
+
+
+def test_ddpm_step_philox_noise_is_the_library_stream(cuda_dev, built_lib):
+    from its_b200 import _lib
+    T, B, n = 30, 3, 256
+    _, coef = _coef(T, cuda_dev)
+    x = torch.zeros(B, n, device=cuda_dev)
+    e = torch.zeros(B, n, device=cuda_dev)
+    t = 11
+    t_dev = torch.tensor([t], dtype=torch.int32, device=cuda_dev)
+    flag = torch.zeros(1, dtype=torch.int32, device=cuda_dev)
+    _lib.check(built_lib.its_ddpm_step(x.data_ptr(), e.data_ptr(), None, None, 0, B, n, coef.data_ptr(),
+                                       t_dev.data_ptr(), 0.0, 77, 4, flag.data_ptr(), 0, _lib.stream_ptr()))
+    ref = coef[t, 2].item() * philox.normal(77, 4, t, B, n)
+    assert np.abs(x.cpu().numpy() - ref).max() < 1e-4
+
+
+# ------------------------------------------------------------ GroupNorm ------
+@pytest.mark.parametrize("B,H,C0,C1,silu", [(2, 32, 64, 0, True), (3, 16, 128, 64, True), (8, 4, 512, 512, True),
+                                            (2, 8, 384, 0, False), (1, 64, 128, 128, True)])
+def test_group_norm(cuda_dev, built_lib, B, H, C0, C1, silu):
+    from its_b200.engine import UNetPlan
+    g = torch.Generator().manual_seed(B * 1000 + C0 + C1)
+    x0 = (torch.randn(B, C0, H, H, generator=g) * 2 + 0.5).to(cuda_dev)
+    x1 = (torch.randn(B, C1, H, H, generator=g) * 0.5 - 1).to(cuda_dev) if C1 else None
+    gn = torch.nn.GroupNorm(32, C0 + C1).to(cuda_dev)
+    with torch.no_grad():
+        gn.weight.copy_(1 + 0.2 * torch.randn(C0 + C1, generator=g))
+        gn.bias.copy_(0.1 * torch.randn(C0 + C1, generator=g))
+    plan = UNetPlan.scratch(cuda_dev, B)
+    srcs = [nhwc(x0)] + ([nhwc(x1)] if C1 else [])
+    out = plan.group_norm(srcs, gn, silu)
+    plan.run()
+    xin = torch.cat([bf(x0)] + ([bf(x1)] if C1 else []), 1)
+    with torch.no_grad():
+        ref = gn(xin)
+        ref = ref * torch.sigmoid(ref) if silu else ref
+    check_close(nchw(out), ref, 6e-3, "group_norm")
+
+
+# ----------------------------------------------------------- head / tail -----
+def test_conv_head_and_tail(cuda_dev, built_lib):
+    from its_b200 import _lib
+    g = torch.Generator().manual_seed(5)
+    B, H, ch = 4, 16, 64
+    x = torch.randn(2, 3, H, H, generator=g).to(cuda_dev) * 30      # x_t is large at early steps
+    w = torch.randn(ch, 3, 3, 3, generator=g).to(cuda_dev) * 0.2
+    b = torch.randn(ch, generator=g).to(cuda_dev) * 0.1
+    out = torch.empty(B, H, H, ch, dtype=torch.bfloat16, device=cuda_dev)
+    _lib.check(built_lib.its_conv_head(out.data_ptr(), x.data_ptr(), w.data_ptr(), b.data_ptr(), B, 2, H, H, 3, ch,
+                                       _lib.stream_ptr()))
+    ref = F.conv2d(torch.cat([x, x]), w, b, padding=1)
+    check_close(nchw(out), ref, 5e-3, "head")
+    a = torch.randn(B, ch, H, H, generator=g).to(cuda_dev)
+    wt = torch.randn(3, ch, 3, 3, generator=g).to(cuda_dev) * 0.05
+    bt = torch.randn(3, generator=g).to(cuda_dev)
+    eps = torch.empty(B, 3, H, H, device=cuda_dev)
+    _lib.check(built_lib.its_conv_tail(eps.data_ptr(), nhwc(a).data_ptr(), wt.data_ptr(), bt.data_ptr(), B, H, H, ch, 3,
+                                       _lib.stream_ptr()))
+    check_close(eps, F.conv2d(bf(a), wt, bt, padding=1), 1e-5, "tail")
+
+
+# -------------------------------------------------------------- tap-GEMM -----
+def _conv_case(dev, impl, B, H, Cin, Cout, *, k=3, stride=1, extras=False, seed=0):
+    from its_b200.engine import UNetPlan, pack_conv_weight, taps_square
+    g = torch.Generator().manual_seed(seed + 17 * B + H + Cin + Cout)
+    x = torch.randn(B, Cin, H, H, generator=g).to(dev)
+    w = (torch.randn(Cout, Cin, k, k, generator=g) / math.sqrt(Cin * k * k)).to(dev)
+    bias = torch.randn(Cout, generator=g).to(dev)
+    plan = UNetPlan.scratch(dev, B, impl)
+    kw = {}
+    Ho = H // stride
+    ref = F.conv2d(bf(x), bf(w), bias, stride=stride, padding=k // 2)
+    if extras:
+        vec = torch.randn(B, Cout + 8, generator=g).to(dev)
+        vec2 = torch.randn(1, Cout, generator=g).to(dev)
+        res = torch.randn(B, Cout, Ho, Ho, generator=g).to(dev)
+        kw = dict(vec=vec, vec_off=8, vec2=vec2, res=nhwc(res), alpha=0.5)
+        ref = 0.5 * F.conv2d(bf(x), bf(w), None, stride=stride, padding=k // 2) + bias.view(1, -1, 1, 1) \
+            + vec[:, 8:].view(B, Cout, 1, 1) + vec2.view(1, Cout, 1, 1) + bf(res)
+    wp = pack_conv_weight(w).to(torch.bfloat16).contiguous()
+    out = plan.conv([(nhwc(x), Cin, 0, stride, False)], [(taps_square(k), 0, 0, 0)], Ho, Ho, wp, Cout, bias=bias, **kw)
+    plan.run()
+    torch.cuda.synchronize()
+    return nchw(out), ref
+
+
+CONV_SHAPES = [
+    # B, H, Cin, Cout, k, stride, extras
+    (2, 32, 64, 64, 3, 1, False),      # bn=64, 8 tiles per image
+    (2, 32, 128, 128, 3, 1, True),     # bn=128 + full epilogue
+    (2, 16, 256, 256, 3, 1, False),    # bn=256
+    (4, 8, 128, 192, 3, 1, True),      # bn=192, two images per tile
+    (8, 4, 512, 512, 3, 1, False),     # eight images per tile, 72 k-blocks
+    (3, 8, 64, 128, 3, 1, False),      # ragged last tile (batch not a multiple of the box)
+    (2, 4, 128, 128, 3, 1, False),     # box larger than the batch
+    (2, 64, 128, 128, 3, 1, False),    # 64x64 rows: box 64x2
+    (2, 16, 128, 384, 1, 1, True),     # 1x1, three N tiles
+    (2, 32, 128, 128, 3, 2, False),    # DownSample stride 2 (TMA element strides)
+    (4, 16, 256, 256, 3, 2, True),
+    (2, 32, 64, 64, 5, 2, False),      # 5x5 stride 2
+]
+
+
+@pytest.mark.parametrize("impl", [1, 0], ids=["cudacore", "tcgen05"])
+@pytest.mark.parametrize("B,H,Cin,Cout,k,stride,extras", CONV_SHAPES)
+def test_conv_igemm_vs_torch(cuda_dev, built_lib, impl, B, H, Cin, Cout, k, stride, extras):
+    got, ref = _conv_case(cuda_dev, impl, B, H, Cin, Cout, k=k, stride=stride, extras=extras)
+    check_close(got, ref, 6e-3, f"conv impl={impl}")
+
+
+@pytest.mark.parametrize("impl", [1, 0], ids=["cudacore", "tcgen05"])
+def test_conv_fused_shortcut_three_sources(cuda_dev, built_lib, impl):
+    """ResBlock conv2 + 1x1 shortcut over the (h | skip) concat as extra K (Model.py:191-207)."""
+    from its_b200.engine import UNetPlan, pack_conv_weight, taps_square
+    g = torch.Generator().manual_seed(9)
+    B, H, C, Ch, Cs = 2, 16, 128, 128, 64
+    a2 = torch.randn(B, C, H, H, generator=g).to(cuda_dev)
+    h = torch.randn(B, Ch, H, H, generator=g).to(cuda_dev)
+    sk = torch.randn(B, Cs, H, H, generator=g).to(cuda_dev)
+    w2 = (torch.randn(C, C, 3, 3, generator=g) / 34).to(cuda_dev)
+    ws = (torch.randn(C, Ch + Cs, 1, 1, generator=g) / 14).to(cuda_dev)
+    bias = torch.randn(C, generator=g).to(cuda_dev)
+    plan = UNetPlan.scratch(cuda_dev, B, impl)
+    wp = torch.cat([pack_conv_weight(w2), ws[:, :, 0, 0]], 1).to(torch.bfloat16).contiguous()
+    taps = taps_square(3) + [(1, 0, 0), (2, 0, 0)]
+    out = plan.conv([(nhwc(a2), C, 0, 1, False), (nhwc(h), Ch, 0, 1, False), (nhwc(sk), Cs, 0, 1, False)],
+                    [(taps, 0, 0, 0)], H, H, wp, C, bias=bias)
+    plan.run()
+    ref = F.conv2d(bf(a2), bf(w2), bias, padding=1) + F.conv2d(torch.cat([bf(h), bf(sk)], 1), bf(ws))
+    check_close(nchw(out), ref, 6e-3, "fused shortcut")
+
+
+class _Holder:
+    pass
+
+
+@pytest.mark.parametrize("impl", [1, 0], ids=["cudacore", "tcgen05"])
+@pytest.mark.parametrize("kind", ["down_uncond", "down_cond", "up_uncond", "up_cond"])
+def test_resample_blocks(cuda_dev, built_lib, impl, kind):
+    """DownSample / UpSample of both networks through the engine's own block builders."""
+    from its_b200.engine import UNetPlan
+    torch.manual_seed(3)
+    B, H, C = 2, 16, 128
+    x = torch.randn(B, C, H, H, device=cuda_dev)
+    plan = UNetPlan.scratch(cuda_dev, B, impl)
+    m = _Holder()
+    xb = bf(x)
+    with torch.no_grad():
+        if kind == "down_uncond":
+            m.main = torch.nn.Conv2d(C, C, 3, 2, 1).to(cuda_dev)
+            out = plan._down(m, nhwc(x))
+            ref = F.conv2d(xb, bf(m.main.weight), m.main.bias, stride=2, padding=1)
+        elif kind == "down_cond":
+            m.c1 = torch.nn.Conv2d(C, C, 3, 2, 1).to(cuda_dev)
+            m.c2 = torch.nn.Conv2d(C, C, 5, 2, 2).to(cuda_dev)
+            out = plan._down(m, nhwc(x))
+            ref = F.conv2d(xb, bf(m.c1.weight), m.c1.bias, stride=2, padding=1) + \
+                F.conv2d(xb, bf(m.c2.weight), m.c2.bias, stride=2, padding=2)
+        elif kind == "up_uncond":
+            m.main = torch.nn.Conv2d(C, C, 3, 1, 1).to(cuda_dev)
+            out = plan._up(m, nhwc(x))
+            ref = F.conv2d(F.interpolate(xb, scale_factor=2, mode="nearest"), m.main.weight, m.main.bias, padding=1)
+        else:
+            m.c = torch.nn.Conv2d(C, C, 3, 1, 1).to(cuda_dev)
+            m.t = torch.nn.ConvTranspose2d(C, C, 5, 2, 2, 1).to(cuda_dev)
+            out = plan._up(m, nhwc(x))
+            y = F.conv_transpose2d(xb, bf(m.t.weight), m.t.bias, stride=2, padding=2, output_padding=1)
+            ref = F.conv2d(bf(y), bf(m.c.weight), m.c.bias, padding=1)
+        plan.run()
+    tol = 1.2e-2 if kind == "up_uncond" else 8e-3   # folded weights are summed before bf16 rounding
+    check_close(nchw(out), ref, tol, kind)
+
+
+@pytest.mark.parametrize("impl", [1, 0], ids=["cudacore", "tcgen05"])
+@pytest.mark.parametrize("B,H,C", [(2, 16, 128), (2, 16, 64), (8, 8, 128), (8, 4, 512), (1, 32, 128)])
+def test_attention_block(cuda_dev, built_lib, impl, B, H, C):
+    """AttnBlock (Model.py:145-164): tensor-core batched GEMM path for >= 128 tokens,
+    one-kernel path for small maps."""
+    from its_b200.engine import UNetPlan
+    torch.manual_seed(B * 100 + H + C)
+    at = _Holder()
+    at.group_norm = torch.nn.GroupNorm(32, C).to(cuda_dev)
+    for nme in ("proj_q", "proj_k", "proj_v", "proj"):
+        conv = torch.nn.Conv2d(C, C, 1).to(cuda_dev)
+        with torch.no_grad():
+            conv.weight.mul_(3.0)
+        setattr(at, nme, conv)
+    x = torch.randn(B, C, H, H, device=cuda_dev)
+    plan = UNetPlan.scratch(cuda_dev, B, impl)
+    if H * H > 64 and impl == 1:
+        pytest.skip("large-N attention is defined on the tensor-core path only")
+    with torch.no_grad():
+        out = plan._attn_block(at, nhwc(x))
+        plan.run()
+        sd = {"a.group_norm.weight": at.group_norm.weight, "a.group_norm.bias": at.group_norm.bias}
+        for nme in ("proj_q", "proj_k", "proj_v", "proj"):
+            sd[f"a.{nme}.weight"] = getattr(at, nme).weight
+            sd[f"a.{nme}.bias"] = getattr(at, nme).bias
+        ref = O._attn(sd, "a", bf(x), O._Q(None))
+    check_close(nchw(out), ref, 1.5e-2, "attention")
+
+
+def test_softmax_rows(cuda_dev, built_lib):
+    from its_b200 import _lib
+    s = torch.randn(300, 256, device=cuda_dev) * 4
+    p = torch.empty(300, 256, dtype=torch.bfloat16, device=cuda_dev)
+    _lib.check(built_lib.its_softmax_rows(p.data_ptr(), s.data_ptr(), 300, 256, _lib.stream_ptr()))
+    check_close(p.float(), torch.softmax(s, -1), 5e-3, "softmax")
+
+
+# ------------------------------------------------------- embeddings ----------
+def test_time_embed_and_linear(cuda_dev, built_lib):
+    from its_b200 import _lib
+    ch, B = 128, 5
+    freq = torch.exp(-(torch.arange(0, ch, 2).float() / ch * math.log(10000))).to(cuda_dev)
+    t = torch.tensor([0, 1, 999, 1999, 2999], dtype=torch.int64, device=cuda_dev)
+    out = torch.empty(B, ch, device=cuda_dev)
+    _lib.check(built_lib.its_time_embed(out.data_ptr(), t.data_ptr(), None, freq.data_ptr(), B, ch, _lib.stream_ptr()))
+    emb = t.float()[:, None] * freq[None]
+    ref = torch.stack([torch.sin(emb), torch.cos(emb)], -1).reshape(B, ch)
+    assert (out - ref).abs().max().item() < 2e-4      # fp32 argument up to ~3e3 rad
+    t_dev = torch.tensor([999], dtype=torch.int32, device=cuda_dev)
+    out1 = torch.empty(1, ch, device=cuda_dev)
+    _lib.check(built_lib.its_time_embed(out1.data_ptr(), None, t_dev.data_ptr(), freq.data_ptr(), 1, ch, _lib.stream_ptr()))
+    assert torch.equal(out1[0], out[2])
+    W = torch.randn(512, ch, device=cuda_dev) / 11
+    b = torch.randn(512, device=cuda_dev)
+    y = torch.empty(B, 512, device=cuda_dev)
+    _lib.check(built_lib.its_linear(y.data_ptr(), out.data_ptr(), W.data_ptr(), b.data_ptr(), B, ch, 512, 1, 1, 0,
+                                    _lib.stream_ptr()))
+    r = F.linear(F.silu(out), W, b)
+    assert (y - F.silu(r)).abs().max().item() < 1e-4
+    table = torch.randn(11, ch, device=cuda_dev)
+    idx = torch.tensor([0, 10, 3, 3, 7], dtype=torch.int64, device=cuda_dev)
+    rows = torch.empty(B, ch, device=cuda_dev)
+    _lib.check(built_lib.its_embed_rows(rows.data_ptr(), table.data_ptr(), idx.data_ptr(), None, B, ch, 11, _lib.stream_ptr()))
+    assert torch.equal(rows, table[idx])
+
+
+# -------------------------------------------------------- verifiers ----------
+def test_verifier_kernels_vs_golden_and_oracle(cuda_dev, built_lib):
+    from its_b200.search import verifier as V
+    from tests.util import golden
+    g = golden("verifier")
+    for i, im in enumerate(cases.verifier_images()):
+        d = im.to(cuda_dev)
+        assert abs(V.OracleVerifier().score(d) - float(g[f"oracle_{i}"])) < 1e-3
+        assert abs(V.AestheticPredictor().score(d) - float(g[f"aesthetic_{i}"])) < 1e-3
+        a, b = V.SelfSupervisedVerifier().score(d), float(g[f"self_supervised_{i}"])
+        assert (math.isnan(a) and math.isnan(b)) or abs(a - b) < 1e-3
+        f = V.SelfSupervisedVerifier().extract_features(d)
+        assert (f.cpu() - F.adaptive_avg_pool2d(im, (8, 8)).flatten(1)).abs().max().item() < 1e-5
+    # per-candidate scores of a population == per-call scores of each candidate
+    pop = torch.cat([im for im in cases.verifier_images()[:1]] * 3).to(cuda_dev) * torch.linspace(0.2, 1, 12, device=cuda_dev).view(12, 1, 1, 1)
+    for ver, fn in ((V.OracleVerifier(), O.oracle_verifier_score), (V.AestheticPredictor(), O.aesthetic_score),
+                    (V.SelfSupervisedVerifier(), O.self_supervised_score)):
+        s = ver.score_candidates(pop, 4).cpu()
+        for c in range(3):
+            assert abs(s[c].item() - fn(pop[4 * c:4 * c + 4].cpu())) < 1e-3
+    assert V.OracleVerifier(dataset_stats={"mu": 0}).score(pop) == pytest.approx(pop.mean().item(), abs=1e-5)
+
+
+def test_argmax_first(cuda_dev, built_lib):
+    from its_b200.search.search_algorithm import argmax_first
+    nan, inf = float("nan"), float("inf")
+    assert argmax_first(torch.tensor([0.5, nan, 0.7, 0.7, 0.1], device=cuda_dev)) == (2, pytest.approx(0.7))
+    assert argmax_first(torch.tensor([nan, nan], device=cuda_dev)) == (-1, -inf)
+    assert argmax_first(torch.tensor([-inf, -inf], device=cuda_dev)) == (-1, -inf)
+    s = torch.randn(70000, device=cuda_dev)
+    s[[123, 60000]] = 9.0
+    assert argmax_first(s) == (123, 9.0)
+    assert argmax_first(torch.tensor([3.0], device=cuda_dev)) == (0, 3.0)

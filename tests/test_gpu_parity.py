@@ -1,0 +1,230 @@
+"""GPU: the CUDA path end to end (UNet plan, fused sampler, verifiers, search)
+against the committed fixtures of the reference's own outputs (tests/golden/) and
+against the CPU oracle on the same seeded inputs.
+
+Tolerances (north_star): samples within max-abs 2e-2 in bf16; verifier scores
+within 1e-3; selected candidate index exact whenever the top-2 margin exceeds
+the score tolerance."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ddpm_oracle as O
+from tests import cases
+from tests.util import build_shell, golden, rel_err, rms_err
+
+pytestmark = pytest.mark.gpu
+
+SAMPLE_TOL = 2e-2
+SCORE_TOL = 1e-3
+
+
+@pytest.mark.parametrize("impl", [1, 0], ids=["cudacore", "tcgen05"])
+@pytest.mark.parametrize("name", ["u_small", "u_3lvl", "c_small"])
+def test_unet_forward_small_vs_reference_and_emulation(cuda_dev, impl, name):
+    cfg = cases.FORWARD_CASES[name]
+    net, sd = build_shell(cfg, cuda_dev)
+    net.impl = impl
+    x, t, labels = cases.forward_inputs(cfg)
+    args = (x.to(cuda_dev), t.to(cuda_dev)) + ((labels.to(cuda_dev),) if labels is not None else ())
+    eps = net(*args).cpu()
+    ref = torch.from_numpy(golden("fwd_" + name)["eps"])
+    assert eps.shape == ref.shape and torch.isfinite(eps).all()
+    # against the fp32 reference: bf16 storage noise only
+    assert rms_err(eps, ref) < 1.5e-2, (rms_err(eps, ref), rel_err(eps, ref))
+    assert rel_err(eps, ref) < 6e-2
+    # against the oracle with the same storage rounding: kernel arithmetic itself
+    with torch.no_grad():
+        emu = O.unet_forward(sd, x, t, labels, quant="bf16")
+    assert rms_err(eps, emu) < 6e-3, (rms_err(eps, emu), rel_err(eps, emu))
+
+
+@pytest.mark.parametrize("name", ["u_A", "u_E", "c_C"])
+def test_unet_forward_full_size_vs_reference(cuda_dev, name):
+    """BASELINE configs A (CIFAR 32x32), E (64x64) and C (CFG net) at their real widths."""
+    cfg = cases.FORWARD_CASES[name]
+    net, _ = build_shell(cfg, cuda_dev)
+    x, t, labels = cases.forward_inputs(cfg)
+    args = (x.to(cuda_dev), t.to(cuda_dev)) + ((labels.to(cuda_dev),) if labels is not None else ())
+    eps = net(*args).cpu()
+    ref = torch.from_numpy(golden("fwd_" + name)["eps"])
+    assert torch.isfinite(eps).all()
+    assert rms_err(eps, ref) < 2e-2, (rms_err(eps, ref), rel_err(eps, ref))
+    assert rel_err(eps, ref) < 8e-2
+
+
+def test_unet_forward_is_batch_invariant_and_deterministic(cuda_dev):
+    """A candidate's eps must not depend on which batch / rank evaluates it."""
+    cfg = cases.FORWARD_CASES["u_3lvl"]
+    net, _ = build_shell(cfg, cuda_dev)
+    x, t, _ = cases.forward_inputs(cfg)
+    x, t = x.to(cuda_dev), t.to(cuda_dev)
+    full = net(x, t)
+    again = net(x, t)
+    assert torch.equal(full, again)
+    halves = torch.cat([net(x[:4], t[:4]), net(x[4:], t[4:])])
+    assert torch.equal(full, halves)
+
+
+@pytest.mark.parametrize("name", ["u_small_T20", "c_small_T20"])
+@pytest.mark.parametrize("graph", [False, True], ids=["eager", "cudagraph"])
+def test_sampler_injected_noise_vs_reference(cuda_dev, name, graph):
+    cfg = cases.SAMPLER_CASES[name]
+    net, sd = build_shell(cfg, cuda_dev)
+    x_T, noise, labels = cases.sampler_inputs(cfg)
+    if cfg["kind"] == "uncond":
+        from its_b200.Diffusion import GaussianDiffusionSampler
+        smp = GaussianDiffusionSampler(net, cfg["beta_1"], cfg["beta_T"], cfg["T"]).to(cuda_dev)
+        call = lambda: smp(x_T.to(cuda_dev), noise=noise.to(cuda_dev))          # noqa: E731
+    else:
+        from its_b200.DiffusionFreeGuidence import GaussianDiffusionSampler
+        smp = GaussianDiffusionSampler(net, cfg["beta_1"], cfg["beta_T"], cfg["T"], w=cfg["w"]).to(cuda_dev)
+        call = lambda: smp(x_T.to(cuda_dev), labels.to(cuda_dev), noise=noise.to(cuda_dev))   # noqa: E731
+    smp.print_steps = False
+    smp.use_cuda_graph = graph
+    x0 = call().cpu()
+    g = golden("smp_" + name)
+    ref = torch.from_numpy(g["x0"])
+    assert x0.min() >= -1 and x0.max() <= 1
+    err = (x0 - ref).abs().max().item()
+    assert err <= SAMPLE_TOL, f"max abs {err}"
+    x0b = call().cpu()                      # second trajectory re-uses the captured graph
+    assert torch.equal(x0, x0b)
+    from its_b200.search import verifier as V
+    d = x0.to(cuda_dev)
+    assert abs(V.OracleVerifier().score(d) - float(g["score_oracle"])) <= SCORE_TOL
+    assert abs(V.AestheticPredictor().score(d) - float(g["score_aesthetic"])) <= SCORE_TOL
+    assert abs(V.SelfSupervisedVerifier().score(d) - float(g["score_self_supervised"])) <= SCORE_TOL
+
+
+def test_p_mean_variance_seam(cuda_dev):
+    """The public seam the reference's own external loop drives (Diffusion/Train.py:68-77)."""
+    cfg = cases.SAMPLER_CASES["u_small_T20"]
+    net, sd = build_shell(cfg, cuda_dev)
+    from its_b200.Diffusion import GaussianDiffusionSampler
+    smp = GaussianDiffusionSampler(net, cfg["beta_1"], cfg["beta_T"], cfg["T"]).to(cuda_dev)
+    smp.print_steps = False
+    x_T, noise, _ = cases.sampler_inputs(cfg)
+    x_t = x_T.to(cuda_dev)
+    for time_step in reversed(range(cfg["T"])):
+        t = x_t.new_ones([x_t.shape[0]], dtype=torch.long) * time_step
+        mean, var = smp.p_mean_variance(x_t=x_t, t=t)
+        assert var.shape == (x_t.shape[0], 1, 1, 1)
+        z = noise[time_step].to(cuda_dev) if time_step > 0 else 0
+        x_t = mean + torch.sqrt(var) * z
+    ext = torch.clip(x_t, -1, 1).cpu()
+    ref = torch.from_numpy(golden("smp_u_small_T20")["x0"])
+    assert (ext - ref).abs().max().item() <= SAMPLE_TOL
+    fused = smp(x_T.to(cuda_dev), noise=noise.to(cuda_dev)).cpu()
+    assert (ext - fused).abs().max().item() <= 1e-5     # same kernels, same arithmetic
+
+
+def test_sampler_philox_streams(cuda_dev):
+    """In-kernel noise: reproducible per seed, keyed by global candidate id (rank-count invariant)."""
+    cfg = cases.SAMPLER_CASES["u_small_T20"]
+    net, _ = build_shell(cfg, cuda_dev)
+    from its_b200.Diffusion import GaussianDiffusionSampler
+    smp = GaussianDiffusionSampler(net, cfg["beta_1"], cfg["beta_T"], cfg["T"]).to(cuda_dev)
+    smp.print_steps = False
+    x_T = torch.randn(4, 3, 32, 32, generator=torch.Generator().manual_seed(0)).to(cuda_dev)
+    a = smp(x_T, seed=5, cand_id0=0)
+    b = smp(x_T, seed=5, cand_id0=0)
+    c = smp(x_T, seed=6, cand_id0=0)
+    assert torch.equal(a, b) and not torch.equal(a, c)
+    assert torch.isfinite(a).all() and a.abs().max() <= 1
+    halves = torch.cat([smp(x_T[:2], seed=5, cand_id0=0), smp(x_T[2:], seed=5, cand_id0=2)])
+    assert torch.equal(a, halves)
+    with pytest.raises(AssertionError, match="nan in tensor"):
+        smp(torch.full_like(x_T, float("nan")), seed=1)
+
+
+def _search_setup(cfg, dev):
+    net, sd = build_shell(cfg, dev)
+    if cfg["kind"] == "uncond":
+        from its_b200.Diffusion import GaussianDiffusionSampler
+        smp = GaussianDiffusionSampler(net, cfg["beta_1"], cfg["beta_T"], cfg["T"]).to(dev)
+    else:
+        from its_b200.DiffusionFreeGuidence import GaussianDiffusionSampler
+        smp = GaussianDiffusionSampler(net, cfg["beta_1"], cfg["beta_T"], cfg["T"], w=cfg["w"]).to(dev)
+    smp.print_steps = False
+    from its_b200.search import search_algorithm as S
+    from its_b200.search import verifier as V
+    ver = {"oracle": V.OracleVerifier(), "aesthetic": V.AestheticPredictor(),
+           "self_supervised": V.SelfSupervisedVerifier()}[cfg["verifier"]]
+    labels = cases.search_labels(cfg)
+    den = S.make_denoise_fn(smp, None if labels is None else labels.to(dev),
+                            step_noise=cases.search_noise(cfg).to(dev), seed=1)
+    return S, den, ver
+
+
+def _margin(scores):
+    s = sorted([x for x in scores if not math.isnan(x)], reverse=True)
+    return s[0] - s[1] if len(s) > 1 else float("inf")
+
+
+@pytest.mark.parametrize("name", ["u_search", "c_search"])
+def test_search_selection_vs_reference(cuda_dev, name):
+    """Random / zero-order / path search through the reference's class surface,
+    population mode, candidates injected exactly as the reference drew them."""
+    cfg = cases.SEARCH_CASES[name]
+    g = golden("search_" + name)
+    S, den, ver = _search_setup(cfg, cuda_dev)
+    shape = tuple(cfg["noise_shape"])
+    # ---- random search
+    rs = S.RandomSearch(n_candidates=cfg["n_candidates"])
+    cand = torch.from_numpy(g["rs_candidates"]).to(cuda_dev)
+    best_noise, best_score = rs.search(shape, den, ver.score, device="cuda", verbose=False, candidate_noise=cand)
+    got = rs.last_scores.cpu().numpy()
+    assert np.abs(got - g["rs_scores"]).max() <= SCORE_TOL, (got, g["rs_scores"])
+    assert rs.nfes == cfg["n_candidates"]
+    if _margin(list(g["rs_scores"])) > 2 * SCORE_TOL:
+        assert rs.last_index == int(g["rs_best_index"])
+        assert torch.equal(best_noise, cand[int(g["rs_best_index"])])
+        assert abs(best_score - float(g["rs_best_score"])) <= SCORE_TOL
+    # callable mode (arbitrary callables): the reference's serial loop, same answer
+    rs2 = S.RandomSearch(n_candidates=cfg["n_candidates"])
+    bn2, bs2 = rs2.search(shape, lambda z, show_progress=False, **kw: den(z), lambda im, **kw: ver.score(im),
+                          device="cuda", verbose=False, candidate_noise=cand)
+    assert abs(bs2 - best_score) <= 1e-6 and torch.equal(bn2, best_noise)
+    # ---- zero-order search
+    zo = S.ZeroOrderSearch(n_neighbors=cfg["zo_neighbors"], lambda_radius=0.95, n_iterations=cfg["zo_iterations"])
+    init = torch.from_numpy(g["zo_init"]).to(cuda_dev)
+    perts = torch.from_numpy(g["zo_perts"]).to(cuda_dev)
+    zn, zs, zh = zo.search(init, den, ver.score, device="cuda", perturbations=perts)
+    assert np.abs(np.array(zh["scores"]) - g["zo_scores"]).max() <= SCORE_TOL
+    assert zh["candidates_per_iter"] == [cfg["zo_neighbors"]] * cfg["zo_iterations"]
+    if all(_margin(list(r)) > 2 * SCORE_TOL for r in g["zo_scores"]):
+        assert abs(zs - float(g["zo_best_score"])) <= SCORE_TOL
+        assert (zn.cpu() - torch.from_numpy(g["zo_best_noise"])).abs().max().item() < 1e-6
+    # ---- path search (reference placeholder semantics)
+    ps = S.PathSearch(n_paths=cfg["n_paths"], injection_step=cfg["T"] // 2, noise_scale=0.1)
+    var = torch.from_numpy(g["ps_variations"]).to(cuda_dev)
+    pn, pscore, ph = ps.search(init, den, ver.score, timesteps=cfg["T"], device="cuda", variations=var)
+    assert np.abs(np.array(ph["scores"]) - g["ps_scores"]).max() <= SCORE_TOL
+    assert ph["injection_points"] == [cfg["T"] // 2] * cfg["n_paths"]
+    if _margin(list(g["ps_scores"])) > 2 * SCORE_TOL:
+        assert abs(pscore - float(g["ps_best_score"])) <= SCORE_TOL
+        assert (pn.cpu() - torch.from_numpy(g["ps_best_noise"])).abs().max().item() < 1e-6
+
+
+def test_random_search_philox_population(cuda_dev):
+    """Throughput-mode candidates (in-kernel Philox): reproducible, winner regenerated from its id."""
+    cfg = cases.SEARCH_CASES["u_search"]
+    S, den, ver = _search_setup(cfg, cuda_dev)
+    den.step_noise = None
+    den.max_images = 8           # forces several sampler batches
+    shape = tuple(cfg["noise_shape"])
+    rs = S.RandomSearch(n_candidates=10)
+    n1, s1 = rs.search(shape, den, ver.score, device="cuda", verbose=False, seed=42)
+    sc1 = rs.last_scores.clone()
+    den.max_images = 64          # one batch: same numbers (batch invariance)
+    n2, s2 = rs.search(shape, den, ver.score, device="cuda", verbose=False, seed=42)
+    assert torch.equal(sc1, rs.last_scores) and torch.equal(n1, n2) and s1 == s2
+    # the returned noise really is the winner: denoise it alone and score it
+    img = den.denoise_candidates(n1.unsqueeze(0), rs.last_index)[0]
+    assert abs(ver.score(img) - s1) < 1e-6
+    ps = S.PathSearch(n_paths=3, injection_step=cfg["T"] // 2, noise_scale=0.1)
+    pn, pscore, ph = ps.search(n1, den, ver.score, timesteps=cfg["T"], device="cuda", seed=7, restart=True)
+    assert len(ph["scores"]) == 3 and math.isfinite(pscore)
