@@ -1,0 +1,326 @@
+#!/usr/bin/env python
+"""Headline benchmark: candidate images / second of the inference-time-scaling
+sampling path (BASELINE.json: "candidate images/sec (T=1000 NFE, verifier incl.)").
+
+One "step" = one complete random search over the candidate population owned by a
+GPU: every candidate runs the full T=1000 DDPM ancestral loop over the
+unconditional CIFAR-10 UNet (config A/B of SURVEY.md §8), the finished samples are
+scored by the verifier kernels and the best one is selected by the first-index
+argmax (+ one all_gather of the scores when several GPUs take part).
+
+    python bench.py --gpus 1 --steps K --warmup W                (our CUDA path)
+    torchrun ... bench.py --gpus N --steps K --warmup W          (one rank per GPU, weak scaling)
+    python bench.py --impl reference --steps K --warmup W        (the reference's CPU path)
+
+Prints ONE JSON line (rank 0).  `value` is device-timed with the candidates
+already resident in HBM; `e2e` goes through the public search API with the
+candidate noise in pinned HOST memory (H2D inside the timed region) and the
+scores + winning noise read back (D2H).  `roofline` is the tcgen05 tap-GEMM
+family, timed launch by launch with CUDA events; `cpu_baseline` is the CPU port
+of the reference path (oracle/) on this box's host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import contextlib
+import io
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "candidate images/sec (T=1000 NFE, verifier incl.)"
+UNIT = "images/s"
+CFG_A = dict(T=1000, ch=128, ch_mult=[1, 2, 3, 4], attn=[1], num_res_blocks=2, dropout=0.15)
+BETA_1, BETA_T = 1e-4, 0.02
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(source="measured (MEASURED_PEAKS.json)", hbm=p["hbm_gbs"], burst=p["bf16_tflops"],
+                    sustained=p.get("bf16_tflops_sustained", p["bf16_tflops"]))
+    return dict(source="fallback (B200_PROFILING.md)", hbm=6650.0, burst=1590.0, sustained=1400.0)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            self.proc.terminate()
+            self.thread.join(timeout=2)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------ CPU arm --
+def cpu_reference_sample(batch: int, n_steps: int, seed: int = 0):
+    """The reference's CPU path (oracle port, all host threads): `n_steps` of the
+    T=1000 ancestral loop for config A at `batch` images + the verifier; returns
+    (seconds, extrapolated candidate images/s for the full T=1000 trajectory)."""
+    from oracle import ddpm_oracle as O
+    from its_b200.Diffusion import UNet
+    torch.manual_seed(seed)
+    net = UNet(**CFG_A)                          # same constructor/initialisers as the reference
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    sched = O.schedule(BETA_1, BETA_T, CFG_A["T"])
+    x = torch.randn(batch, 3, 32, 32)
+    t0 = time.perf_counter()
+    with torch.no_grad(), contextlib.redirect_stdout(io.StringIO()):
+        x0 = O.sample(sd, sched, x, lambda s: torch.randn(batch, 3, 32, 32), t_start=CFG_A["T"] - 1
+                      if n_steps >= CFG_A["T"] else None) if n_steps >= CFG_A["T"] else _partial(O, sd, sched, x, n_steps)
+        O.oracle_verifier_score(torch.clip(x0, -1, 1))
+    dt = time.perf_counter() - t0
+    full = dt * CFG_A["T"] / min(n_steps, CFG_A["T"])
+    return dt, batch / full
+
+
+def _partial(O, sd, sched, x, n_steps):
+    T = CFG_A["T"]
+    for time_step in range(T - 1, T - 1 - n_steps, -1):
+        t = torch.full((x.shape[0],), time_step, dtype=torch.long)
+        mean, var, _ = O.p_mean_variance(sd, sched, x, t)
+        x = mean + torch.sqrt(var) * torch.randn_like(x)
+    return x
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = torch.get_num_threads()
+    batch, n_steps = 8, args.ref_steps
+    vals, secs = [], []
+    for i in range(args.warmup + args.steps):
+        dt, v = cpu_reference_sample(batch, n_steps, seed=i)
+        if i >= args.warmup:
+            vals.append(v); secs.append(dt)
+    value = statistics.mean(vals)
+    sample = (f"oracle port of Diffusion.py:84-102 + verifier.py:62, config A, batch {batch}, {n_steps} of 1000 "
+              f"denoising steps per bench step, extrapolated x{1000 // n_steps} (loop is step-homogeneous)")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * statistics.mean(secs), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, 1),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, world):
+    return {"workload": "random_search_N64_uncond_cifar10_T1000 (BASELINE.json configs[1])",
+            "unet": "Model.UNet ch=128 ch_mult=[1,2,3,4] attn=[1] num_res_blocks=2, random init",
+            "candidates_per_gpu": args.candidates, "noise_shape": [1, 3, 32, 32], "T": CFG_A["T"],
+            "verifier": "OracleVerifier", "selection": "argmax_first", "global_candidates": args.candidates * world,
+            "parallelism": f"candidate-sharded x{world}",
+            "l2": "per-step working set (163 MB bf16 weights + >1 GB activations per UNet pass) exceeds the 126 MB L2"}
+
+
+# ------------------------------------------------------------------ GPU arm --
+def run_ours(args):
+    import __graft_entry__ as ge
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    if not os.path.exists(ge.LIB_PATH):
+        if rank == 0:
+            ge.build()
+        if world > 1:
+            dist.barrier()
+    from its_b200.Diffusion import GaussianDiffusionSampler, UNet
+    from its_b200.search import search_algorithm as S
+    from its_b200.search import verifier as V
+
+    torch.manual_seed(0)
+    net = UNet(**CFG_A).to(dev).eval()
+    smp = GaussianDiffusionSampler(net, BETA_1, BETA_T, CFG_A["T"]).to(dev)
+    smp.print_steps = False
+    n_local, n_total = args.candidates, args.candidates * world
+    shape = (1, 3, 32, 32)
+    den = S.make_denoise_fn(smp, max_images=args.candidates, seed=1234)
+    ver = V.OracleVerifier()
+    rs = S.RandomSearch(n_candidates=n_total)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- value: candidates resident in HBM, device timed ----
+    resident = S.philox_normal((n_total,) + shape, 1234, 0, S.TAG_X_T, dev)
+
+    def step_resident():
+        return rs.search(shape, den, ver.score, device=str(dev), verbose=False, candidate_noise=resident, seed=1234)
+
+    for _ in range(args.warmup):
+        step_resident()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        e0.record()
+        for _ in range(args.steps):
+            best_noise, best_score = step_resident()
+        e1.record()
+        barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_per_step = ms.item() / args.steps
+    value = n_total / (ms_per_step / 1e3)
+    launches_per_traj = smp.last_launches_per_step * CFG_A["T"]
+    gpu_launches = args.steps * (launches_per_traj + 4)   # + image_stats, candidate_scores, argmax, (philox)
+
+    # ---- e2e: public API, candidates in pinned host memory, results read back ----
+    host = resident.cpu().pin_memory()
+    scores_host = torch.empty(n_total, dtype=torch.float32).pin_memory()
+
+    def step_e2e():
+        lo, hi = S._shard(n_total, rank, world)
+        cand = torch.empty_like(resident)
+        cand[lo:hi].copy_(host[lo:hi], non_blocking=True)            # H2D of this rank's candidates
+        bn, bs = rs.search(shape, den, ver.score, device=str(dev), verbose=False, candidate_noise=cand, seed=1234)
+        scores_host.copy_(rs.last_scores, non_blocking=True)         # D2H
+        out = host[rs.last_index].clone()                            # winner is already on the host
+        torch.cuda.synchronize()
+        return out, bs
+
+    step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    barrier()
+    dt = torch.tensor([time.perf_counter() - t0], device=dev)
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    e2e_value = n_total * args.steps / dt.item()
+    h2d = n_local * 3 * 32 * 32 * 4
+    d2h = n_total * 4 + 8
+
+    # ---- roofline of the dominant kernel family: every tap-GEMM launch timed with events ----
+    pk = peaks()
+    plan = net.plan(n_local, 32, 32, n_img_in=n_local, uniform_t=True)
+    roof = profile_tapgemm(plan, dev, pk)
+    roof["step_share"] = roof.pop("sum_ms") * CFG_A["T"] / ms_per_step if ms_per_step else None
+    roof["model_flops_frac_of_sustained"] = (value / world) * plan.flops / n_local * CFG_A["T"] / (pk["sustained"] * 1e12)
+
+    line = None
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            cores = torch.get_num_threads()
+            dt_cpu, v_cpu = cpu_reference_sample(8, args.ref_steps)
+            cpu = {"value": v_cpu, "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": f"oracle port, config A, batch 8, {args.ref_steps} of 1000 steps ({dt_cpu:.1f} s), extrapolated"}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic", "config": workload_config(args, world),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": gpu_launches, "roofline": roof, "cpu_baseline": cpu, "clocks": clocks.summary(),
+            "best_score": best_score,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return line
+
+
+def profile_tapgemm(plan, dev, pk):
+    """Run the plan launch by launch; CUDA-event time every tcgen05 tap-GEMM launch."""
+    from its_b200 import _lib
+    stream = _lib.stream_ptr()
+    for _ in range(2):
+        plan.run()
+    torch.cuda.synchronize()
+    evs = []
+    for (fn, a), (kind, flops, _) in zip(plan.ops, plan.op_info):
+        if kind == "tapgemm_sm100":
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record(); fn(*a, stream); e.record()
+            evs.append((s, e, flops))
+        else:
+            fn(*a, stream)
+    torch.cuda.synchronize()
+    tot_ms = sum(s.elapsed_time(e) for s, e, _ in evs)
+    tot_fl = sum(f for _, _, f in evs)
+    achieved = tot_fl / (tot_ms * 1e-3) / 1e12 if tot_ms > 0 else 0.0
+    return {"bound": "tensor", "kernel": "tapgemm_sm100_kernel (tcgen05 implicit-GEMM conv / batched GEMM)",
+            "achieved": achieved, "peak": pk["burst"], "unit": "TFLOP/s", "frac": achieved / pk["burst"],
+            "peak_source": pk["source"] + ", bf16 burst (kernels timed one by one)", "peak_sustained": pk["sustained"],
+            "launches_per_unet_pass": len(evs), "flops_per_unet_pass": tot_fl, "sum_ms": tot_ms, "traffic": None}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--candidates", type=int, default=64, help="candidates per GPU (weak scaling)")
+    ap.add_argument("--ref-steps", type=int, default=20, help="denoising steps per CPU sample (of T=1000)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

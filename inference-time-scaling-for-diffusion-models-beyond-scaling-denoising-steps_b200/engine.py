@@ -60,6 +60,7 @@ class UNetPlan:
         self.keep: List[torch.Tensor] = []      # everything the launches point into
         self.descs: List[ConvDesc] = []
         self.ops: List[Tuple] = []
+        self.op_info: List[Tuple[str, int, int]] = []   # (kind, algorithmic flops, launches) per op
         self.n_launches = 0
         self.flops = 0                           # algorithmic 2*MAC of the tensor-core GEMMs + linears
         with torch.no_grad():
@@ -75,7 +76,7 @@ class UNetPlan:
         self.model, self.cond = None, False
         self.n_img, self.H, self.W, self.n_img_in = int(n_img), 0, 0, int(n_img)
         self.uniform_t, self.dev, self.impl_forced = False, torch.device(device), impl
-        self.keep, self.descs, self.ops = [], [], []
+        self.keep, self.descs, self.ops, self.op_info = [], [], [], []
         self.n_launches, self.flops = 0, 0
         self.gn_partials, self.tproj, self.cproj = None, None, None
         return self
@@ -91,9 +92,11 @@ class UNetPlan:
         self.keep.append(t)
         return t
 
-    def _op(self, fn, *args, launches: int = 1):
+    def _op(self, fn, *args, launches: int = 1, flops: int = 0, kind: str = "other"):
         self.ops.append((fn, args))
+        self.op_info.append((kind, flops, launches))
         self.n_launches += launches
+        self.flops += flops
 
     # --------------------------------------------------------- primitives --
     def _impl_for(self, chans: Sequence[int], cout: int) -> int:
@@ -115,12 +118,13 @@ class UNetPlan:
             s.ptr, s.c_pitch, s.c_off, s.C = t.data_ptr(), t.shape[-1], c_off, c_used
             s.H, s.W, s.stride, s.bcast = t.shape[1], t.shape[2], stride, int(bcast)
         d.nphases = len(phases)
+        flops = 0
         for i, (taps, w_k0, py, px) in enumerate(phases):
             ph = d.phase[i]
             ph.ntaps, ph.w_k0, ph.py, ph.px = len(taps), w_k0, py, px
             for j, (si, dy, dx) in enumerate(taps):
                 ph.src[j], ph.dy[j], ph.dx[j] = si, dy, dx
-            self.flops += 2 * B * Hm * Wm * cout * sum(srcs[si][1] for si, _, _ in taps)
+            flops += 2 * B * Hm * Wm * cout * sum(srcs[si][1] for si, _, _ in taps)
         d.B, d.Hm, d.Wm = B, Hm, Wm
         d.w, d.w_pitch, d.w_batch_stride, d.Cout = w.data_ptr(), (w_pitch or w.shape[-1]), w_batch_stride, cout
         Hout, Wout = Hm * out_scale, Wm * out_scale
@@ -138,7 +142,8 @@ class UNetPlan:
         d.alpha, d.bn = alpha, 0
         impl = self._impl_for([s[1] for s in srcs], cout)
         self.descs.append(d)
-        self._op(self.L.its_conv_igemm, C.byref(d), impl)
+        self._op(self.L.its_conv_igemm, C.byref(d), impl, flops=flops,
+                 kind="tapgemm_sm100" if impl == 0 else "tapgemm_cudacore")
         return out
 
     def group_norm(self, srcs: Sequence[torch.Tensor], gn, silu: bool) -> torch.Tensor:
@@ -159,7 +164,8 @@ class UNetPlan:
         gamma, beta = self._hold(gn.weight, torch.float32), self._hold(gn.bias, torch.float32)
         self._op(self.L.its_group_norm, out.data_ptr(), x0.data_ptr(), C0, _ptr(x1), C1, gamma.data_ptr(),
                  beta.data_ptr(), B, HW, gn.num_groups, float(gn.eps), int(silu),
-                 self.gn_partials.data_ptr(), chunks, launches=2)
+                 self.gn_partials.data_ptr(), chunks, launches=2, kind="group_norm")
+        self.gn_bytes = getattr(self, "gn_bytes", 0) + B * HW * Ct * 2 * 3   # two reads + one write, bf16
         return out
 
     def linear(self, x: torch.Tensor, W: torch.Tensor, b: Optional[torch.Tensor], *, silu_in=False,
@@ -168,8 +174,7 @@ class UNetPlan:
         N = W.shape[0]
         y = self._new((rows, N), torch.float32)
         self._op(self.L.its_linear, y.data_ptr(), x.data_ptr(), W.data_ptr(), _ptr(b), rows, K, N,
-                 int(silu_in), int(silu_out), 0)
-        self.flops += 2 * rows * K * N
+                 int(silu_in), int(silu_out), 0, flops=2 * rows * K * N, kind="linear")
         return y
 
     # ------------------------------------------------------------- blocks --
@@ -213,7 +218,7 @@ class UNetPlan:
         wq, wk, wv = (m.weight.detach().float()[:, :, 0, 0] for m in (at.proj_q, at.proj_k, at.proj_v))
         bq, bk, bv = (m.bias.detach().float() for m in (at.proj_q, at.proj_k, at.proj_v))
         one = [(0, 0, 0)]
-        tensor_path = (N % 128 == 0) and self._impl_for([Cc, N], Cc) == 0
+        tensor_path = N > 64      # batched-GEMM formulation (tcgen05, or its CUDA-core twin when forced)
         if tensor_path:
             wqk = self._hold(torch.cat([wq, wk], 0), BF16)
             bqk = self._hold(torch.cat([bq, bk], 0), torch.float32)
@@ -227,20 +232,17 @@ class UNetPlan:
             S = self.conv([(qk, Cc, 0, 1, False)], [(one, 0, 0, 0)], H, W, k_view, N, alpha=scale,
                           out_fp32=True, w_batch_stride=N * 2 * Cc, w_pitch=2 * Cc)
             P = self._new((B, H, W, N))
-            self._op(self.L.its_softmax_rows, P.data_ptr(), S.data_ptr(), B * N, N)
+            self._op(self.L.its_softmax_rows, P.data_ptr(), S.data_ptr(), B * N, N, kind="softmax")
             bvh = self._hold(bv, torch.float32)
             o = self.conv([(P, N, 0, 1, False)], [(one, 0, 0, 0)], H, W, vT.view(B, Cc, N), Cc, bias=bvh,
                           w_batch_stride=Cc * N)
         else:
-            if N > 64:
-                raise RuntimeError(f"attention with {N} tokens and {Cc} channels has no kernel "
-                                   "(needs C % 64 == 0 and N % 128 == 0, or N <= 64)")
             wqkv = self._hold(torch.cat([wq, wk, wv], 0), BF16)
             bqkv = self._hold(torch.cat([bq, bk, bv], 0), torch.float32)
             qkv = self.conv([(a, Cc, 0, 1, False)], [(one, 0, 0, 0)], H, W, wqkv, 3 * Cc, bias=bqkv)
             o = self._new((B, H, W, Cc))
-            self._op(self.L.its_attention_small, o.data_ptr(), qkv.data_ptr(), B, N, Cc, scale)
-            self.flops += 4 * B * N * N * Cc
+            self._op(self.L.its_attention_small, o.data_ptr(), qkv.data_ptr(), B, N, Cc, scale,
+                     flops=4 * B * N * N * Cc, kind="attention_small")
         wp = self._hold(at.proj.weight.detach().float()[:, :, 0, 0], BF16)
         bp = self._hold(at.proj.bias, torch.float32)
         return self.conv([(o, Cc, 0, 1, False)], [(one, 0, 0, 0)], H, W, wp, Cc, bias=bp, res=x)
@@ -350,8 +352,7 @@ class UNetPlan:
         h = self._new((B, H, W, ch))
         hw, hb = self._hold(m.head.weight, torch.float32), self._hold(m.head.bias, torch.float32)
         self._op(L.its_conv_head, h.data_ptr(), self.x_in.data_ptr(), hw.data_ptr(), hb.data_ptr(), B,
-                 self.n_img_in, H, W, 3, ch)
-        self.flops += 2 * B * H * W * ch * 27
+                 self.n_img_in, H, W, 3, ch, flops=2 * B * H * W * ch * 27, kind="conv_head")
         hs = [h]
         for layer in m.downblocks:
             h = self._res_block(layer, [h], offs[id(layer)]) if hasattr(layer, "temb_proj") else self._down(layer, h)
@@ -368,8 +369,7 @@ class UNetPlan:
         self.eps = self._new((B, 3, H, W), torch.float32)
         tw, tb = self._hold(m.tail[2].weight, torch.float32), self._hold(m.tail[2].bias, torch.float32)
         self._op(L.its_conv_tail, self.eps.data_ptr(), a.data_ptr(), tw.data_ptr(), tb.data_ptr(), B, a.shape[1],
-                 a.shape[2], a.shape[3], 3)
-        self.flops += 2 * B * H * W * 3 * 9 * a.shape[3]
+                 a.shape[2], a.shape[3], 3, flops=2 * B * H * W * 3 * 9 * a.shape[3], kind="conv_tail")
 
     # ---------------------------------------------------------------- run --
     def run(self) -> None:
