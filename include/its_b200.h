@@ -113,8 +113,10 @@ int its_linear(float* y, const float* x, const float* W, const float* bias,
  * GroupNorm(32 groups) [+ Swish] over the channel concatenation of up to two
  * NHWC bf16 tensors, written as one NHWC bf16 tensor of C0+C1 channels
  * (Model.py:170-173,186-190,132,257-259 and the skip concat Model.py:279-280).
- * Two launches: per-chunk partial sums (deterministic, no float atomics), then
- * finalize+apply.  `partials` is scratch of n_img*chunks*groups*2 floats.
+ * Deterministic (no float atomics).  chunks <= 8: ONE launch, the chunks of an
+ * image form a thread-block cluster and exchange partial sums through distributed
+ * shared memory; chunks > 8: two launches through `partials`, scratch of
+ * n_img*chunks*groups*2 floats.
  * ---------------------------------------------------------------------- */
 int its_group_norm(void* out, const void* src0, int32_t C0, const void* src1,
                    int32_t C1, const float* gamma, const float* beta,
@@ -152,6 +154,9 @@ int its_conv_tail(float* out, const void* act, const float* W,
  * Packed weights Wp are bf16 [Cout][w_pitch], K ordered (phase, tap, channel).
  * impl: 0 = tcgen05/TMA kernel, 1 = CUDA-core reference kernel (same maths;
  * debug and shapes with C % 64 != 0).
+ * Layers with few output tiles (4x4 / 8x8 feature maps) can split K over
+ * `splits` CTAs per tile: partial fp32 accumulators go to `ws` and a second
+ * launch reduces them in a fixed order and applies the epilogue (deterministic).
  * ---------------------------------------------------------------------- */
 typedef struct {
   const void* ptr;       /* bf16 [B][H][W][c_pitch]                      */
@@ -195,7 +200,11 @@ typedef struct {
   const void* res;       /* bf16, out's pixel mapping, or NULL           */
   int32_t res_c_pitch, res_c_off;
   float alpha;
-  int32_t bn;            /* N tile: 0 = auto, else 64/128/192/256        */
+  int32_t bn;            /* N tile: 0 = auto, else 32/64/128/192/256     */
+  int32_t out_nchw;      /* 1: out is fp32 [B][Cout][Hout][Wout] (tail)  */
+  int32_t splits;        /* split-K factor (tcgen05 path); 0/1 = none    */
+  float* ws;             /* split-K scratch: nphases*splits*rows*Cout    */
+  int64_t ws_elems;      /* capacity of ws in floats                     */
 } its_conv_desc;
 
 int its_conv_igemm(const its_conv_desc* desc_host, int32_t impl, void* stream);

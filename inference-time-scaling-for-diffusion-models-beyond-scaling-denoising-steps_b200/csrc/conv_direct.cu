@@ -8,44 +8,61 @@ namespace its {
 
 // ---------------------------------------------------------------- head ----
 // out NHWC bf16 [n_img][H][W][Cout]; x NCHW fp32 [n_img_in][Cin][H][W];
-// W OIHW fp32 [Cout][Cin][3][3].  One thread = one pixel x 8 output channels.
+// W OIHW fp32 [Cout][Cin][3][3].  One thread = one pixel: its Cin*9 inputs stay in
+// registers, the weights are read from shared memory as warp-wide broadcasts
+// (a warp = 32 consecutive pixels, all on the same 16 output channels).
+template <int CIN>
 __global__ void __launch_bounds__(256) conv_head_kernel(
     __nv_bfloat16* __restrict__ out, const float* __restrict__ x, const float* __restrict__ W,
-    const float* __restrict__ bias, int n_img, int n_img_in, int H, int Wd, int Cin, int Cout) {
-  extern __shared__ float s_w[];  // [Cin*9][Cout]
-  const int K = Cin * 9;
+    const float* __restrict__ bias, int n_img, int n_img_in, int H, int Wd, int Cout) {
+  extern __shared__ float s_w[];  // [CIN*9][Cout] then bias[Cout]
+  constexpr int K = CIN * 9;
   for (int i = threadIdx.x; i < K * Cout; i += blockDim.x) {
     const int co = i / K, k = i - co * K;  // W[co][ci][ky][kx] flat = co*K + k
     s_w[k * Cout + co] = W[i];
   }
+  float* s_b = s_w + K * Cout;
+  for (int i = threadIdx.x; i < Cout; i += blockDim.x) s_b[i] = bias ? bias[i] : 0.f;
   __syncthreads();
-  const int nv = Cout / 8;
-  const long long total = (long long)n_img * H * Wd * nv;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int cov = (int)(i % nv);
-    const long long pix = i / nv;
+  const long long npix = (long long)n_img * H * Wd;
+  for (long long pix = blockIdx.x * (long long)blockDim.x + threadIdx.x; pix < npix;
+       pix += (long long)gridDim.x * blockDim.x) {
     const int xw = (int)(pix % Wd);
     const int y = (int)((pix / Wd) % H);
     const int b = (int)(pix / ((long long)Wd * H));
-    const float* xin = x + (long long)(b % n_img_in) * Cin * H * Wd;
-    float acc[8];
+    const float* xin = x + (long long)(b % n_img_in) * CIN * H * Wd;
+    float in[K];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = bias ? bias[cov * 8 + j] : 0.f;
-    for (int ci = 0; ci < Cin; ++ci)
-      for (int ky = 0; ky < 3; ++ky) {
-        const int yy = y + ky - 1;
-        if (yy < 0 || yy >= H) continue;
+    for (int ci = 0; ci < CIN; ++ci)
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
         for (int kx = 0; kx < 3; ++kx) {
-          const int xx = xw + kx - 1;
-          if (xx < 0 || xx >= Wd) continue;
-          const float v = __ldg(xin + ((long long)ci * H + yy) * Wd + xx);
-          const float* wr = s_w + ((ci * 3 + ky) * 3 + kx) * Cout + cov * 8;
+          const int yy = y + ky - 1, xx = xw + kx - 1;
+          const bool inb = (yy >= 0 && yy < H && xx >= 0 && xx < Wd);
+          in[(ci * 3 + ky) * 3 + kx] = inb ? __ldg(xin + ((long long)ci * H + yy) * Wd + xx) : 0.f;
+        }
+    __nv_bfloat16* orow = out + pix * Cout;
+    for (int c0 = 0; c0 < Cout; c0 += 16) {
+      float acc[16];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) acc[j] = fmaf(v, wr[j], acc[j]);
+      for (int j = 0; j < 16; ++j) acc[j] = s_b[c0 + j];
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        const float4* wr = reinterpret_cast<const float4*>(s_w + k * Cout + c0);
+        const float v = in[k];
+#pragma unroll
+        for (int j4 = 0; j4 < 4; ++j4) {
+          const float4 w4 = wr[j4];
+          acc[4 * j4 + 0] = fmaf(v, w4.x, acc[4 * j4 + 0]);
+          acc[4 * j4 + 1] = fmaf(v, w4.y, acc[4 * j4 + 1]);
+          acc[4 * j4 + 2] = fmaf(v, w4.z, acc[4 * j4 + 2]);
+          acc[4 * j4 + 3] = fmaf(v, w4.w, acc[4 * j4 + 3]);
         }
       }
-    *reinterpret_cast<bf16x8*>(out + pix * Cout + cov * 8) = pack8(acc);
+      *reinterpret_cast<bf16x8*>(orow + c0) = pack8(acc);
+      *reinterpret_cast<bf16x8*>(orow + c0 + 8) = pack8(acc + 8);
+    }
   }
 }
 
@@ -126,7 +143,10 @@ __global__ void __launch_bounds__(128) tapgemm_ref_kernel(const TapGemmParams p)
   if (p.vec2) v += p.vec2[(long long)b * p.vec2_stride + n];
   const long long opix = ((long long)b * p.Hout + (y * p.out_scale + ph.py)) * p.Wout + (x * p.out_scale + ph.px);
   if (p.res) v += __bfloat162float(p.res[opix * p.res_c_pitch + n]);
-  if (p.out_fp32)
+  if (p.out_nchw)
+    static_cast<float*>(p.out)[(((long long)b * p.Cout + n) * p.Hout + (y * p.out_scale + ph.py)) * p.Wout +
+                               (x * p.out_scale + ph.px)] = v;
+  else if (p.out_fp32)
     static_cast<float*>(p.out)[opix * p.out_c_pitch + n] = v;
   else
     static_cast<__nv_bfloat16*>(p.out)[opix * p.out_c_pitch + n] = __float2bfloat16_rn(v);
@@ -182,7 +202,17 @@ int tapgemm_build_params(const its_conv_desc* d, TapGemmParams* p, bool need_k64
   p->B = d->B; p->Hm = d->Hm; p->Wm = d->Wm;
   p->w = static_cast<const __nv_bfloat16*>(d->w);
   p->w_pitch = d->w_pitch; p->w_batch_stride = d->w_batch_stride; p->Cout = d->Cout;
-  ITS_REQUIRE(d->out_c_pitch >= d->out_c_off + d->Cout, "its_conv_igemm: out channel pitch");
+  ITS_REQUIRE(d->out_nchw || d->out_c_pitch >= d->out_c_off + d->Cout, "its_conv_igemm: out channel pitch");
+  ITS_REQUIRE(!d->out_nchw || (d->out_fp32 && d->out_c_off == 0 && d->res == nullptr),
+              "its_conv_igemm: out_nchw needs fp32 output, no channel offset, no residual");
+  p->out_nchw = d->out_nchw;
+  p->splits = d->splits > 1 ? d->splits : 1;
+  p->ws = d->ws;
+  if (p->splits > 1) {
+    ITS_REQUIRE(d->ws != nullptr, "its_conv_igemm: splits=%d needs a workspace", d->splits);
+    const long long need = (long long)d->nphases * p->splits * d->B * d->Hm * d->Wm * d->Cout;
+    ITS_REQUIRE(d->ws_elems >= need, "its_conv_igemm: workspace has %lld floats, %lld needed", (long long)d->ws_elems, need);
+  }
   p->out_fp32 = d->out_fp32;
   p->out = d->out_fp32 ? static_cast<void*>(static_cast<float*>(d->out) + d->out_c_off)
                        : static_cast<void*>(static_cast<__nv_bfloat16*>(d->out) + d->out_c_off);
@@ -219,15 +249,15 @@ extern "C" int its_conv_head(void* out, const float* x, const float* W, const fl
                              int32_t Cout, void* stream) {
   using namespace its;
   ITS_REQUIRE(out && x && W, "its_conv_head: null pointer");
-  ITS_REQUIRE(n_img > 0 && n_img_in > 0 && H > 0 && Wd > 0 && Cin > 0 && Cin <= 4 && Cout % 8 == 0 && Cout > 0,
-              "its_conv_head: unsupported shape Cin=%d Cout=%d", Cin, Cout);
-  const size_t smem = (size_t)Cin * 9 * Cout * sizeof(float);
+  ITS_REQUIRE(n_img > 0 && n_img_in > 0 && H > 0 && Wd > 0 && Cin == 3 && Cout % 16 == 0 && Cout > 0,
+              "its_conv_head: unsupported shape Cin=%d Cout=%d (Cin must be 3, Cout a multiple of 16)", Cin, Cout);
+  const size_t smem = ((size_t)Cin * 9 + 1) * Cout * sizeof(float);
   ITS_REQUIRE(smem <= 48 * 1024, "its_conv_head: Cout=%d too large", Cout);
-  const long long total = (long long)n_img * H * Wd * (Cout / 8);
-  long long blocks = (total + 255) / 256;
+  const long long npix = (long long)n_img * H * Wd;
+  long long blocks = (npix + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
-  conv_head_kernel<<<(unsigned)blocks, 256, smem, as_stream(stream)>>>(
-      static_cast<__nv_bfloat16*>(out), x, W, bias, n_img, n_img_in, H, Wd, Cin, Cout);
+  conv_head_kernel<3><<<(unsigned)blocks, 256, smem, as_stream(stream)>>>(
+      static_cast<__nv_bfloat16*>(out), x, W, bias, n_img, n_img_in, H, Wd, Cout);
   ITS_CHECK_LAUNCH();
   return ITS_OK;
 }

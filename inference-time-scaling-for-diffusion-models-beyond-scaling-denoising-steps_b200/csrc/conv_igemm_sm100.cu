@@ -132,6 +132,54 @@ __host__ __device__ constexpr uint32_t make_idesc(int bn) {
 
 __host__ __device__ constexpr int tmem_cols_for(int bn) { return bn <= 32 ? 32 : bn <= 64 ? 64 : bn <= 128 ? 128 : 256; }
 
+// alpha / bias / per-image vectors / residual, then the store in one of the three
+// output formats.  f[8] holds raw accumulators of columns n..n+7 of GEMM row (b,y,x).
+__device__ __forceinline__ void apply_and_store8(const TapGemmParams& p, const DevPhase& ph, int b, int y,
+                                                 int x, int n, float* f) {
+  const int yo = y * p.out_scale + ph.py, xo = x * p.out_scale + ph.px;
+  if (p.out_nchw) {  // thin outputs (the 3-channel tail): element-wise guards, coalesced over pixels
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (n + j < p.Cout) {
+        float v = f[j] * p.alpha;
+        if (p.bias) v += __ldg(p.bias + n + j);
+        static_cast<float*>(p.out)[(((long long)b * p.Cout + n + j) * p.Hout + yo) * p.Wout + xo] = v;
+      }
+    }
+    return;
+  }
+  const long long opix = ((long long)b * p.Hout + yo) * p.Wout + xo;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) f[j] *= p.alpha;
+  if (p.bias) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] += __ldg(p.bias + n + j);
+  }
+  if (p.vec) {
+    const float* v = p.vec + (long long)b * p.vec_stride + n;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] += __ldg(v + j);
+  }
+  if (p.vec2) {
+    const float* v = p.vec2 + (long long)b * p.vec2_stride + n;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] += __ldg(v + j);
+  }
+  if (p.res) {
+    float r[8];
+    unpack8(*reinterpret_cast<const bf16x8*>(p.res + opix * p.res_c_pitch + n), r);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] += r[j];
+  }
+  if (p.out_fp32) {
+    float4* dst = reinterpret_cast<float4*>(static_cast<float*>(p.out) + opix * p.out_c_pitch + n);
+    dst[0] = make_float4(f[0], f[1], f[2], f[3]);
+    dst[1] = make_float4(f[4], f[5], f[6], f[7]);
+  } else {
+    *reinterpret_cast<bf16x8*>(static_cast<__nv_bfloat16*>(p.out) + opix * p.out_c_pitch + n) = pack8(f);
+  }
+}
+
 template <int BN, int STAGES>
 struct SmemLayout {
   static constexpr int B_BYTES = BN * BK * 2;
@@ -155,8 +203,11 @@ tapgemm_sm100_kernel(const __grid_constant__ TapGemmParams p, const __grid_const
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const DevPhase& ph = p.phase[blockIdx.z];
-  const int nkb = ph.nkb;
+  const int phase_idx = blockIdx.z / p.splits, split = blockIdx.z - phase_idx * p.splits;
+  const DevPhase& ph = p.phase[phase_idx];
+  // split-K: this CTA owns k-blocks [kb0, kb1) of the phase
+  const int kb0 = (ph.nkb * split) / p.splits, kb1 = (ph.nkb * (split + 1)) / p.splits;
+  const int nkb = kb1 - kb0;
   const int mt = blockIdx.x;
   const int tx = mt % p.tiles_x;
   const int ty = (mt / p.tiles_x) % p.tiles_y;
@@ -188,16 +239,19 @@ tapgemm_sm100_kernel(const __grid_constant__ TapGemmParams p, const __grid_const
     // ------------------------------------------------ TMA producer ----
     if (lane == 0) {
       const int wb = (p.w_batch_stride != 0) ? tb * p.bb : 0;
-      int kb = 0;
-      for (int t = 0; t < ph.ntaps; ++t) {
+      int g = 0;  // k-block index within the phase
+      for (int t = 0; t < ph.ntaps && g < kb1; ++t) {
         const int si = ph.src[t];
         const DevSrc& s = p.src[si];
+        const int ncb = s.C / BK;
+        if (g + ncb <= kb0) { g += ncb; continue; }
         const CUtensorMap* tm = (si == 0) ? &tmA0 : (si == 1) ? &tmA1 : &tmA2;
         const int cx = tx * p.bw * s.stride + ph.dx[t];
         const int cy = ty * p.bh * s.stride + ph.dy[t];
         const int cb_img = s.bcast ? 0 : tb * p.bb;
-        const int ncb = s.C / BK;
-        for (int cb = 0; cb < ncb; ++cb, ++kb) {
+        for (int cb = 0; cb < ncb; ++cb, ++g) {
+          if (g < kb0 || g >= kb1) continue;
+          const int kb = g - kb0;
           const int stage = kb % STAGES;
           const uint32_t parity = (uint32_t)((kb / STAGES) & 1);
           mbar_wait(&empty_bar[stage], parity ^ 1u);
@@ -205,7 +259,7 @@ tapgemm_sm100_kernel(const __grid_constant__ TapGemmParams p, const __grid_const
           uint8_t* b_dst = a_dst + A_BYTES;
           mbar_expect_tx(&full_bar[stage], (uint32_t)L::STAGE_BYTES);
           tma_load_4d(a_dst, tm, &full_bar[stage], cb * BK, cx, cy, cb_img);
-          tma_load_3d(b_dst, &tmB, &full_bar[stage], ph.w_k0 + kb * BK, n0, wb);
+          tma_load_3d(b_dst, &tmB, &full_bar[stage], ph.w_k0 + g * BK, n0, wb);
         }
       }
     }
@@ -238,10 +292,10 @@ tapgemm_sm100_kernel(const __grid_constant__ TapGemmParams p, const __grid_const
     const int rx = row % p.bw;
     const int b = tb * p.bb + rb, y = ty * p.bh + ry, x = tx * p.bw + rx;
     const bool valid = (b < p.B) && (y < p.Hm) && (x < p.Wm);
-    const long long opix =
-        ((long long)b * p.Hout + (y * p.out_scale + ph.py)) * p.Wout + (x * p.out_scale + ph.px);
-    const float* vec = p.vec ? p.vec + (long long)b * p.vec_stride : nullptr;
-    const float* vec2 = p.vec2 ? p.vec2 + (long long)b * p.vec2_stride : nullptr;
+    const long long grow = ((long long)b * p.Hm + y) * p.Wm + x;   // linear GEMM row
+    float* ws_row = nullptr;
+    if (p.splits > 1)
+      ws_row = p.ws + (((long long)blockIdx.z * p.B * p.Hm * p.Wm) + grow) * p.Cout;
     mbar_wait(tmem_full_bar, 0);
     tcgen05_fence_after();
 #pragma unroll 1
@@ -253,34 +307,17 @@ tapgemm_sm100_kernel(const __grid_constant__ TapGemmParams p, const __grid_const
         for (int g = 0; g < 4; ++g) {
           const int n = n0 + c0 + g * 8;
           if (n < p.Cout) {
-            float f[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[g * 8 + j]) * p.alpha;
-            if (p.bias) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) f[j] += __ldg(p.bias + n + j);
-            }
-            if (vec) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) f[j] += __ldg(vec + n + j);
-            }
-            if (vec2) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) f[j] += __ldg(vec2 + n + j);
-            }
-            if (p.res) {
-              float r[8];
-              unpack8(*reinterpret_cast<const bf16x8*>(p.res + opix * p.res_c_pitch + n), r);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) f[j] += r[j];
-            }
-            if (p.out_fp32) {
-              float4* dst = reinterpret_cast<float4*>(static_cast<float*>(p.out) + opix * p.out_c_pitch + n);
-              dst[0] = make_float4(f[0], f[1], f[2], f[3]);
-              dst[1] = make_float4(f[4], f[5], f[6], f[7]);
+            if (ws_row != nullptr) {   // split-K partial: raw accumulators, reduced by the finalize launch
+              float4* dst = reinterpret_cast<float4*>(ws_row + n);
+              dst[0] = make_float4(__uint_as_float(v[g * 8 + 0]), __uint_as_float(v[g * 8 + 1]),
+                                   __uint_as_float(v[g * 8 + 2]), __uint_as_float(v[g * 8 + 3]));
+              dst[1] = make_float4(__uint_as_float(v[g * 8 + 4]), __uint_as_float(v[g * 8 + 5]),
+                                   __uint_as_float(v[g * 8 + 6]), __uint_as_float(v[g * 8 + 7]));
             } else {
-              *reinterpret_cast<bf16x8*>(static_cast<__nv_bfloat16*>(p.out) + opix * p.out_c_pitch + n) =
-                  pack8(f);
+              float f[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[g * 8 + j]);
+              apply_and_store8(p, ph, b, y, x, n, f);
             }
           }
         }
@@ -295,6 +332,35 @@ tapgemm_sm100_kernel(const __grid_constant__ TapGemmParams p, const __grid_const
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
                  "r"((uint32_t)TMEM_COLS)
                  : "memory");
+  }
+}
+
+// Split-K second pass: sum the `splits` partial tiles in a fixed order, then the
+// same epilogue.  One thread per (phase, GEMM row, 8 output columns).
+__global__ void __launch_bounds__(256) tapgemm_finalize_kernel(const TapGemmParams p) {
+  const int nv = p.Cout / 8;
+  const long long rows = (long long)p.B * p.Hm * p.Wm;
+  const long long total = rows * nv * p.nphases;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % nv);
+    const long long r = (i / nv) % rows;
+    const int phase_idx = (int)(i / (nv * rows));
+    const DevPhase& ph = p.phase[phase_idx];
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = 0.f;
+    for (int s = 0; s < p.splits; ++s) {
+      const float4* src = reinterpret_cast<const float4*>(
+          p.ws + (((long long)(phase_idx * p.splits + s) * rows) + r) * p.Cout + cv * 8);
+      const float4 a = src[0], b4 = src[1];
+      f[0] += a.x; f[1] += a.y; f[2] += a.z; f[3] += a.w;
+      f[4] += b4.x; f[5] += b4.y; f[6] += b4.z; f[7] += b4.w;
+    }
+    const int x = (int)(r % p.Wm);
+    const int y = (int)((r / p.Wm) % p.Hm);
+    const int b = (int)(r / ((long long)p.Wm * p.Hm));
+    apply_and_store8(p, ph, b, y, x, cv * 8, f);
   }
 }
 
@@ -342,26 +408,37 @@ static int launch_variant(const TapGemmParams& p, const CUtensorMap* tmA, const 
     ITS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
     configured = true;
   }
-  dim3 grid(p.tiles_x * p.tiles_y * p.tiles_b, (p.Cout + BN - 1) / BN, p.nphases);
+  dim3 grid(p.tiles_x * p.tiles_y * p.tiles_b, (p.Cout + BN - 1) / BN, p.nphases * p.splits);
   kern<<<grid, NUM_THREADS, L::TOTAL, stream>>>(p, tmA[0], tmA[1], tmA[2], tmB);
   ITS_CHECK_LAUNCH();
+  if (p.splits > 1) {
+    const long long items = (long long)p.B * p.Hm * p.Wm * (p.Cout / 8) * p.nphases;
+    long long blocks = (items + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    tapgemm_finalize_kernel<<<(unsigned)blocks, 256, 0, stream>>>(p);
+    ITS_CHECK_LAUNCH();
+  }
   return ITS_OK;
 }
 
 int tapgemm_launch_sm100(const its_conv_desc* d, const TapGemmParams& p, cudaStream_t stream) {
   // tile N
   int bn = d->bn;
-  if (bn == 0) bn = (p.Cout % 256 == 0) ? 256 : (p.Cout % 192 == 0) ? 192 : (p.Cout % 128 == 0) ? 128 : 64;
-  ITS_REQUIRE(bn == 64 || bn == 128 || bn == 192 || bn == 256, "its_conv_igemm: bn=%d", bn);
-  ITS_REQUIRE(p.Cout % 8 == 0, "its_conv_igemm: Cout=%d must be a multiple of 8", p.Cout);
-  ITS_REQUIRE(p.Cout >= bn || p.Cout % 16 == 0, "its_conv_igemm: Cout=%d", p.Cout);
+  if (bn == 0)
+    bn = (p.Cout % 256 == 0) ? 256 : (p.Cout % 192 == 0) ? 192 : (p.Cout % 128 == 0) ? 128 : (p.Cout > 32) ? 64 : 32;
+  ITS_REQUIRE(bn == 32 || bn == 64 || bn == 128 || bn == 192 || bn == 256, "its_conv_igemm: bn=%d", bn);
+  ITS_REQUIRE(p.out_nchw || p.Cout % 8 == 0, "its_conv_igemm: Cout=%d must be a multiple of 8", p.Cout);
+  ITS_REQUIRE(p.splits == 1 || (!p.out_nchw && p.Cout % 8 == 0), "its_conv_igemm: split-K needs NHWC output");
+  for (int f = 0; f < p.nphases; ++f)
+    ITS_REQUIRE(p.splits <= p.phase[f].nkb, "its_conv_igemm: splits=%d exceeds the %d k-blocks of phase %d", p.splits, p.phase[f].nkb, f);
   ITS_REQUIRE(p.w_pitch % 8 == 0 && p.w_batch_stride % 8 == 0, "its_conv_igemm: weight pitch alignment");
   ITS_REQUIRE((reinterpret_cast<uintptr_t>(p.w) & 15) == 0, "its_conv_igemm: weight pointer alignment");
   ITS_REQUIRE(p.bw * p.bh * p.bb == BM, "its_conv_igemm: Hm=%d Wm=%d do not tile into 128-row boxes", p.Hm, p.Wm);
   ITS_REQUIRE(p.Wm % p.bw == 0 && (p.Hm % p.bh == 0 || p.bh > p.Hm),
               "its_conv_igemm: Hm=%d Wm=%d not divisible by the tile box", p.Hm, p.Wm);
   ITS_REQUIRE(p.w_batch_stride == 0 || p.bb == 1, "its_conv_igemm: per-image weights with a multi-image tile");
-  ITS_REQUIRE(p.out_c_pitch % 8 == 0 && (p.res == nullptr || p.res_c_pitch % 8 == 0), "its_conv_igemm: out/res pitch alignment");
+  ITS_REQUIRE(p.out_nchw || (p.out_c_pitch % 8 == 0 && (p.res == nullptr || p.res_c_pitch % 8 == 0)),
+              "its_conv_igemm: out/res pitch alignment");
 
   CUtensorMap tmA[ITS_MAX_SRC];
   memset(tmA, 0, sizeof(tmA));
@@ -399,6 +476,7 @@ int tapgemm_launch_sm100(const its_conv_desc* d, const TapGemmParams& p, cudaStr
     if (rc != ITS_OK) return rc;
   }
   switch (bn) {
+    case 32:  return launch_variant<32, 4, 2>(p, tmA, tmB, stream);
     case 64:  return launch_variant<64, 4, 2>(p, tmA, tmB, stream);
     case 128: return launch_variant<128, 3, 2>(p, tmA, tmB, stream);
     case 192: return launch_variant<192, 5, 1>(p, tmA, tmB, stream);

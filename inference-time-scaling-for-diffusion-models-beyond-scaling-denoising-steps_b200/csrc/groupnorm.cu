@@ -6,6 +6,7 @@
 // Reference: nn.GroupNorm(32, C) + Swish at Model.py:170-173,186-190,132,257-259;
 // concat at Model.py:279-280.
 #include "its_common.cuh"
+#include <cooperative_groups.h>
 
 namespace its {
 
@@ -127,6 +128,126 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const GnArgs a) {
   }
 }
 
+// Single-launch variant: the `chunks` CTAs of one image form a thread-block
+// cluster, exchange their per-group partial sums through distributed shared memory
+// (fixed rank order -> deterministic) and apply the normalisation to their chunk,
+// which they kept in shared memory (CACHE) — one global read + one write per element.
+template <bool CACHE>
+__global__ void __launch_bounds__(GN_THREADS) gn_cluster_kernel(const GnArgs a) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  extern __shared__ __align__(16) unsigned char gn_dyn[];
+  __shared__ float s_sum[GN_THREADS * 8];
+  __shared__ float s_sq[GN_THREADS * 8];
+  __shared__ float s_part[64 * 2];
+  __shared__ float s_mean[64], s_rstd[64];
+  __nv_bfloat16* cache = reinterpret_cast<__nv_bfloat16*>(gn_dyn);
+  const int nvec = a.C / 8;
+  const int prow = GN_THREADS / nvec;
+  const int tid = threadIdx.x;
+  const int cv = tid % nvec, pl = tid / nvec;
+  const int chunk = blockIdx.x, img = blockIdx.y;
+  const int per = (a.HW + a.chunks - 1) / a.chunks;
+  const int p0 = chunk * per, p1 = min(a.HW, p0 + per);
+  const int cg_ch = a.C / a.groups;
+  float sum[8], sq[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) sum[i] = sq[i] = 0.f;
+  if (pl < prow) {
+    for (int p = p0 + pl; p < p1; p += prow) {
+      const bf16x8 raw = gn_load(a, (long long)img * a.HW + p, cv * 8);
+      if (CACHE) *reinterpret_cast<bf16x8*>(cache + (long long)(p - p0) * a.C + cv * 8) = raw;
+      float f[8];
+      unpack8(raw, f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { sum[i] += f[i]; sq[i] = fmaf(f[i], f[i], sq[i]); }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      s_sum[pl * a.C + cv * 8 + i] = sum[i];
+      s_sq[pl * a.C + cv * 8 + i] = sq[i];
+    }
+  }
+  __syncthreads();
+  const int warp = tid >> 5, lane = tid & 31;
+  for (int g = warp; g < a.groups; g += GN_THREADS / 32) {
+    float ps = 0.f, pq = 0.f;
+    const int n = cg_ch * prow;
+    for (int e = lane; e < n; e += 32) {
+      const int r = e / cg_ch, c = g * cg_ch + (e - r * cg_ch);
+      ps += s_sum[r * a.C + c];
+      pq += s_sq[r * a.C + c];
+    }
+    ps = warp_sum(ps);
+    pq = warp_sum(pq);
+    if (lane == 0) { s_part[2 * g] = ps; s_part[2 * g + 1] = pq; }
+  }
+  cluster.sync();                                  // every CTA's s_part is published
+  if (tid < a.groups) {
+    double s = 0.0, q = 0.0;
+    for (int r = 0; r < a.chunks; ++r) {           // fixed order: identical on all CTAs
+      const float* remote = cluster.map_shared_rank(s_part, r);
+      s += (double)remote[2 * tid];
+      q += (double)remote[2 * tid + 1];
+    }
+    const double n = (double)cg_ch * (double)a.HW;
+    const double mean = s / n;
+    double var = q / n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    s_mean[tid] = (float)mean;
+    s_rstd[tid] = (float)(1.0 / sqrt(var + (double)a.eps));
+  }
+  cluster.sync();                                  // remote reads done before any CTA may exit
+  if (pl >= prow) return;
+  float scale[8], shift[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = cv * 8 + i;
+    const int g = c / cg_ch;
+    const float sc = s_rstd[g] * a.gamma[c];
+    scale[i] = sc;
+    shift[i] = a.beta[c] - s_mean[g] * sc;
+  }
+  for (int p = p0 + pl; p < p1; p += prow) {
+    const long long pix = (long long)img * a.HW + p;
+    float f[8];
+    if (CACHE)
+      unpack8(*reinterpret_cast<const bf16x8*>(cache + (long long)(p - p0) * a.C + cv * 8), f);
+    else
+      unpack8(gn_load(a, pix, cv * 8), f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float v = fmaf(f[i], scale[i], shift[i]);
+      f[i] = a.silu ? silu_f(v) : v;
+    }
+    *reinterpret_cast<bf16x8*>(a.out + pix * a.C + cv * 8) = pack8(f);
+  }
+}
+
+template <bool CACHE>
+static int launch_gn_cluster(const GnArgs& a, int n_img, size_t dyn_bytes, cudaStream_t stream) {
+  auto kern = gn_cluster_kernel<CACHE>;
+  static size_t configured = 0;
+  if (dyn_bytes > configured) {
+    ITS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_bytes));
+    configured = dyn_bytes;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(a.chunks, n_img, 1);
+  cfg.blockDim = dim3(GN_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = dyn_bytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = a.chunks;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  ITS_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, a));
+  return ITS_OK;
+}
+
 }  // namespace its
 
 extern "C" int its_group_norm(void* out, const void* src0, int32_t C0, const void* src1, int32_t C1,
@@ -148,6 +269,13 @@ extern "C" int its_group_norm(void* out, const void* src0, int32_t C0, const voi
   a.gamma = gamma; a.beta = beta; a.partials = partials;
   a.C0 = C0; a.C1 = C1; a.C = C; a.HW = HW; a.groups = groups; a.chunks = chunks; a.silu = silu;
   a.eps = eps;
+  if (chunks <= 8) {
+    // one launch: cluster of `chunks` CTAs per image
+    const int per = (HW + chunks - 1) / chunks;
+    const size_t cache_bytes = (size_t)per * C * 2;
+    if (cache_bytes <= 96 * 1024) return launch_gn_cluster<true>(a, n_img, cache_bytes, as_stream(stream));
+    return launch_gn_cluster<false>(a, n_img, 0, as_stream(stream));
+  }
   dim3 grid(chunks, n_img);
   gn_stats_kernel<<<grid, GN_THREADS, 0, as_stream(stream)>>>(a);
   ITS_CHECK_LAUNCH();

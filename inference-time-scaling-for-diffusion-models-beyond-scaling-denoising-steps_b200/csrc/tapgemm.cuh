@@ -35,6 +35,9 @@ struct TapGemmParams {
   const __nv_bfloat16* res;  // already offset by res_c_off
   int res_c_pitch;
   float alpha;
+  int out_nchw;
+  int splits;                // split-K factor (>= 1)
+  float* ws;                 // [nphases][splits][B*Hm*Wm][Cout] fp32 partial sums
   // M tiling: a 128-row tile is a (bb images) x (bh rows) x (bw cols) box
   int bw, bh, bb, tiles_x, tiles_y, tiles_b;
 };

@@ -79,6 +79,7 @@ class UNetPlan:
         self.keep, self.descs, self.ops, self.op_info = [], [], [], []
         self.n_launches, self.flops = 0, 0
         self.gn_partials, self.tproj, self.cproj = None, None, None
+        self.ws, self.split_k = None, True
         return self
 
     # ------------------------------------------------------------ buffers --
@@ -99,15 +100,36 @@ class UNetPlan:
         self.flops += flops
 
     # --------------------------------------------------------- primitives --
-    def _impl_for(self, chans: Sequence[int], cout: int) -> int:
+    def _impl_for(self, chans: Sequence[int], cout: int, out_nchw: bool = False) -> int:
         if self.impl_forced is not None:
             return self.impl_forced
-        ok = all(c % 64 == 0 for c in chans) and cout % 8 == 0 and cout >= 16
+        ok = all(c % 64 == 0 for c in chans) and (out_nchw or (cout % 8 == 0 and cout >= 16))
         return 0 if ok else 1
+
+    @staticmethod
+    def _tiles(B: int, Hm: int, Wm: int, cout: int, per_image_w: bool) -> Tuple[int, int]:
+        """(M tiles, N tile width) exactly as the library tiles a tap-GEMM (csrc/conv_direct.cu)."""
+        bw = min(Wm, 128)
+        bh = min(Hm, 128 // bw)
+        bb = 128 // (bw * bh)
+        if per_image_w and bb > 1:
+            bh, bb = 128 // bw, 1
+        tiles_m = -(-Wm // bw) * -(-Hm // bh) * -(-B // bb)
+        bn = 256 if cout % 256 == 0 else 192 if cout % 192 == 0 else 128 if cout % 128 == 0 else 64 if cout > 32 else 32
+        return tiles_m, bn
+
+    def _splits_for(self, B, Hm, Wm, cout, nphases, nkb_min, per_image_w) -> int:
+        """Split K when a layer has too few output tiles to fill the 148 SMs (4x4 / 8x8 maps)."""
+        tiles_m, bn = self._tiles(B, Hm, Wm, cout, per_image_w)
+        ctas = tiles_m * -(-cout // bn) * nphases
+        if ctas >= 96:
+            return 1
+        s = min(148 // ctas, nkb_min // 4, 16)
+        return max(1, s)
 
     def conv(self, srcs, phases, Hm, Wm, w, cout, *, out=None, out_scale=1, bias=None, vec=None,
              vec_off=0, vec2=None, vec2_off=0, res=None, alpha=1.0, out_fp32=False, w_batch_stride=0,
-             w_pitch=None, B=None, out_shape=None) -> torch.Tensor:
+             w_pitch=None, B=None, out_shape=None, out_nchw=False) -> torch.Tensor:
         """Append one tap-GEMM launch.  srcs: list of (tensor NHWC, C_used, c_off, stride, bcast);
         phases: list of (taps[(src,dy,dx)], w_k0, py, px)."""
         B = self.n_img if B is None else B
@@ -139,10 +161,20 @@ class UNetPlan:
             d.vec2, d.vec2_stride, d.vec2_off = vec2.data_ptr(), (0 if vec2.shape[0] == 1 else vec2.shape[1]), vec2_off
         if res is not None:
             d.res, d.res_c_pitch, d.res_c_off = res.data_ptr(), res.shape[-1], 0
-        d.alpha, d.bn = alpha, 0
-        impl = self._impl_for([s[1] for s in srcs], cout)
+        d.alpha, d.bn, d.out_nchw = alpha, 0, int(out_nchw)
+        impl = self._impl_for([s[1] for s in srcs], cout, out_nchw)
+        launches = 1
+        if impl == 0 and not out_nchw and self.split_k:
+            nkb_min = min(sum(srcs[si][1] for si, _, _ in taps) // 64 for taps, _, _, _ in phases)
+            splits = self._splits_for(B, Hm, Wm, cout, len(phases), nkb_min, bool(w_batch_stride))
+            if splits > 1:
+                need = len(phases) * splits * B * Hm * Wm * cout
+                if self.ws is None or self.ws.numel() < need:
+                    self.ws = self._new((need,), torch.float32)
+                d.splits, d.ws, d.ws_elems = splits, self.ws.data_ptr(), self.ws.numel()
+                launches = 2
         self.descs.append(d)
-        self._op(self.L.its_conv_igemm, C.byref(d), impl, flops=flops,
+        self._op(self.L.its_conv_igemm, C.byref(d), impl, flops=flops, launches=launches,
                  kind="tapgemm_sm100" if impl == 0 else "tapgemm_cudacore")
         return out
 
@@ -158,14 +190,15 @@ class UNetPlan:
         # the split depends on (HW, C) only, never on the batch: a candidate's numbers are then
         # bit-identical whatever batch / rank it is evaluated in (fixed summation order)
         chunks = max(1, min(HW // prow, 8))
+        chunks = 1 << (chunks.bit_length() - 1)      # cluster of 1/2/4/8 CTAs per image
         need = B * chunks * 32 * 2
         if self.gn_partials is None or self.gn_partials.numel() < need:
             self.gn_partials = self._new((need,), torch.float32)
         gamma, beta = self._hold(gn.weight, torch.float32), self._hold(gn.bias, torch.float32)
         self._op(self.L.its_group_norm, out.data_ptr(), x0.data_ptr(), C0, _ptr(x1), C1, gamma.data_ptr(),
                  beta.data_ptr(), B, HW, gn.num_groups, float(gn.eps), int(silu),
-                 self.gn_partials.data_ptr(), chunks, launches=2, kind="group_norm")
-        self.gn_bytes = getattr(self, "gn_bytes", 0) + B * HW * Ct * 2 * 3   # two reads + one write, bf16
+                 self.gn_partials.data_ptr(), chunks, launches=1, kind="group_norm")
+        self.gn_bytes = getattr(self, "gn_bytes", 0) + B * HW * Ct * 2 * 2   # one read + one write, bf16
         return out
 
     def linear(self, x: torch.Tensor, W: torch.Tensor, b: Optional[torch.Tensor], *, silu_in=False,
@@ -305,6 +338,7 @@ class UNetPlan:
         B, H, W = self.n_img, self.H, self.W
         ch = m.head.out_channels
         self.gn_partials = None
+        self.ws, self.split_k = None, True
         self.x_in = self._new((self.n_img_in, 3, H, W), torch.float32)
         self.t_dev = torch.zeros(1, dtype=torch.int32, device=self.dev)
         self.t_idx = torch.zeros(B, dtype=torch.int64, device=self.dev)
@@ -367,9 +401,18 @@ class UNetPlan:
         assert len(hs) == 0
         a = self.group_norm([h], m.tail[0], silu=True)
         self.eps = self._new((B, 3, H, W), torch.float32)
-        tw, tb = self._hold(m.tail[2].weight, torch.float32), self._hold(m.tail[2].bias, torch.float32)
-        self._op(L.its_conv_tail, self.eps.data_ptr(), a.data_ptr(), tw.data_ptr(), tb.data_ptr(), B, a.shape[1],
-                 a.shape[2], a.shape[3], 3, flops=2 * B * H * W * 3 * 9 * a.shape[3], kind="conv_tail")
+        ct = a.shape[3]
+        if self._impl_for([ct], 3, True) == 0:
+            # 3-channel tail on the tensor cores: N tile of 32 (rows 3..31 of the weight box are
+            # TMA zero fill), epilogue writes NCHW fp32 directly (coalesced over pixels)
+            tw = self._hold(pack_conv_weight(m.tail[2].weight), BF16)
+            tb = self._hold(m.tail[2].bias, torch.float32)
+            self.conv([(a, ct, 0, 1, False)], [(taps_square(3), 0, 0, 0)], H, W, tw, 3, bias=tb, out=self.eps,
+                      out_fp32=True, out_nchw=True)
+        else:
+            tw, tb = self._hold(m.tail[2].weight, torch.float32), self._hold(m.tail[2].bias, torch.float32)
+            self._op(L.its_conv_tail, self.eps.data_ptr(), a.data_ptr(), tw.data_ptr(), tb.data_ptr(), B, a.shape[1],
+                     a.shape[2], ct, 3, flops=2 * B * H * W * 3 * 9 * ct, kind="conv_tail")
 
     # ---------------------------------------------------------------- run --
     def run(self) -> None:

@@ -244,6 +244,46 @@ def test_conv_fused_shortcut_three_sources(cuda_dev, built_lib, impl):
     check_close(nchw(out), ref, 6e-3, "fused shortcut")
 
 
+@pytest.mark.parametrize("impl", [1, 0], ids=["cudacore", "tcgen05"])
+def test_conv_tail_on_tensor_cores_nchw_output(cuda_dev, built_lib, impl):
+    """3-channel tail conv (Model.py:257-262) through the tap-GEMM with the NCHW fp32 epilogue."""
+    from its_b200.engine import UNetPlan, pack_conv_weight, taps_square
+    g = torch.Generator().manual_seed(21)
+    B, H, C = 3, 32, 128
+    a = torch.randn(B, C, H, H, generator=g).to(cuda_dev)
+    w = (torch.randn(3, C, 3, 3, generator=g) / 34).to(cuda_dev)
+    bias = torch.randn(3, generator=g).to(cuda_dev)
+    plan = UNetPlan.scratch(cuda_dev, B, impl)
+    ain = nhwc(a)
+    out = torch.full((B, 3, H, H), float("nan"), device=cuda_dev)
+    plan.conv([(ain, C, 0, 1, False)], [(taps_square(3), 0, 0, 0)], H, H,
+              pack_conv_weight(w).to(torch.bfloat16).contiguous(), 3, bias=bias, out=out, out_fp32=True, out_nchw=True)
+    plan.run()
+    torch.cuda.synchronize()
+    check_close(out, F.conv2d(bf(a), bf(w), bias, padding=1), 2e-3, "tail")
+
+
+def test_split_k_matches_unsplit_bitwise_inputs(cuda_dev, built_lib):
+    """Split-K (few output tiles) against the un-split launch of the same layer."""
+    from its_b200.engine import UNetPlan, pack_conv_weight, taps_square
+    g = torch.Generator().manual_seed(4)
+    B, H, C = 16, 4, 512
+    x = torch.randn(B, C, H, H, generator=g).to(cuda_dev)
+    w = (torch.randn(C, C, 3, 3, generator=g) / 68).to(cuda_dev)
+    xin, wp = nhwc(x), pack_conv_weight(w).to(torch.bfloat16).contiguous()
+    outs = []
+    for split in (True, False):
+        plan = UNetPlan.scratch(cuda_dev, B, 0)
+        plan.split_k = split
+        outs.append(plan.conv([(xin, C, 0, 1, False)], [(taps_square(3), 0, 0, 0)], H, H, wp, C))
+        assert (plan.descs[0].splits > 1) == split
+        plan.run()
+    torch.cuda.synchronize()
+    ref = F.conv2d(bf(x), bf(w), None, padding=1)
+    check_close(nchw(outs[0]), ref, 6e-3, "split")
+    check_close(nchw(outs[0]), nchw(outs[1]), 8e-3, "split vs unsplit")   # fp32 re-association + bf16 rounding
+
+
 class _Holder:
     pass
 
