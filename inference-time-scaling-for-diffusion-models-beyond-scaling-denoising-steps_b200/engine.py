@@ -118,9 +118,14 @@ class UNetPlan:
         bn = 256 if cout % 256 == 0 else 192 if cout % 192 == 0 else 128 if cout % 128 == 0 else 64 if cout > 32 else 32
         return tiles_m, bn
 
+    # The split-K factor changes the fp32 summation order, so it must not depend on the actual
+    # batch: it is derived from the layer shape at this nominal per-GPU population.  A candidate's
+    # numbers are then bit-identical whatever batch / rank evaluates it.
+    DESIGN_BATCH = 64
+
     def _splits_for(self, B, Hm, Wm, cout, nphases, nkb_min, per_image_w) -> int:
         """Split K when a layer has too few output tiles to fill the 148 SMs (4x4 / 8x8 maps)."""
-        tiles_m, bn = self._tiles(B, Hm, Wm, cout, per_image_w)
+        tiles_m, bn = self._tiles(self.DESIGN_BATCH, Hm, Wm, cout, per_image_w)
         ctas = tiles_m * -(-cout // bn) * nphases
         if ctas >= 96:
             return 1

@@ -267,7 +267,7 @@ def test_split_k_matches_unsplit_bitwise_inputs(cuda_dev, built_lib):
     """Split-K (few output tiles) against the un-split launch of the same layer."""
     from its_b200.engine import UNetPlan, pack_conv_weight, taps_square
     g = torch.Generator().manual_seed(4)
-    B, H, C = 16, 4, 512
+    B, H, C = 16, 4, 512      # 4x4 maps: 16 CTAs at the design batch -> split 9
     x = torch.randn(B, C, H, H, generator=g).to(cuda_dev)
     w = (torch.randn(C, C, 3, 3, generator=g) / 68).to(cuda_dev)
     xin, wp = nhwc(x), pack_conv_weight(w).to(torch.bfloat16).contiguous()
