@@ -205,6 +205,8 @@ typedef struct {
   int32_t splits;        /* split-K factor (tcgen05 path); 0/1 = none    */
   float* ws;             /* split-K scratch: nphases*splits*rows*Cout    */
   int64_t ws_elems;      /* capacity of ws in floats                     */
+  int32_t cluster;       /* CTAs per cluster sharing a multicast weight tile:
+                            0 = auto (4/2/1), else 1, 2 or 4             */
 } its_conv_desc;
 
 int its_conv_igemm(const its_conv_desc* desc_host, int32_t impl, void* stream);

@@ -78,6 +78,32 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, ui
         "r"(c2)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_3d_mcast(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0,
+                                                  int c1, int c2, uint16_t cta_mask) {
+  // the box lands at the same CTA-relative offset in every CTA of cta_mask and
+  // completes bytes on the mbarrier at the same offset in each of them
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4, %5}], [%2], %6;"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1),
+        "r"(c2), "h"(cta_mask)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_mcast(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(smem_u32(bar)), "h"(cta_mask)
+      : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
 __device__ __forceinline__ void tcgen05_fence_after() {
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 }
@@ -188,7 +214,12 @@ struct SmemLayout {
   static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 1) * 8 + 8 + 1024;  // + alignment slack
 };
 
-template <int BN, int STAGES, int MIN_CTAS>
+// CS > 1: the CS CTAs of a cluster are consecutive M tiles of the same (N tile, phase,
+// split).  They need the same weight tile, so each loads 1/CS of it and multicasts the
+// slice into all CS shared memories: L2->SM weight traffic drops by CS.  A stage may only
+// be refilled once every CTA of the cluster has consumed it, so the MMA issuers commit to
+// the "empty" barriers of all CS CTAs.
+template <int BN, int STAGES, int MIN_CTAS, int CS>
 __global__ void __launch_bounds__(NUM_THREADS, MIN_CTAS)
 tapgemm_sm100_kernel(const __grid_constant__ TapGemmParams p, const __grid_constant__ CUtensorMap tmA0,
                      const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
@@ -218,7 +249,7 @@ tapgemm_sm100_kernel(const __grid_constant__ TapGemmParams p, const __grid_const
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], CS);
     }
     mbar_init(tmem_full_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -232,8 +263,11 @@ tapgemm_sm100_kernel(const __grid_constant__ TapGemmParams p, const __grid_const
   }
   tcgen05_fence_before();
   __syncthreads();
+  if (CS > 1) cluster_sync_all();   // peers' barriers are initialised before anything remote arrives
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const uint32_t crank = (CS > 1) ? cluster_ctarank() : 0u;
+  constexpr uint16_t kMask = (uint16_t)((1u << CS) - 1u);
 
   if (warp == 0) {
     // ------------------------------------------------ TMA producer ----
@@ -259,7 +293,13 @@ tapgemm_sm100_kernel(const __grid_constant__ TapGemmParams p, const __grid_const
           uint8_t* b_dst = a_dst + A_BYTES;
           mbar_expect_tx(&full_bar[stage], (uint32_t)L::STAGE_BYTES);
           tma_load_4d(a_dst, tm, &full_bar[stage], cb * BK, cx, cy, cb_img);
-          tma_load_3d(b_dst, &tmB, &full_bar[stage], ph.w_k0 + g * BK, n0, wb);
+          if (CS == 1) {
+            tma_load_3d(b_dst, &tmB, &full_bar[stage], ph.w_k0 + g * BK, n0, wb);
+          } else {
+            constexpr int SLICE = BN / CS;   // rows of the weight tile this CTA fetches for everyone
+            tma_load_3d_mcast(b_dst + crank * (SLICE * BK * 2), &tmB, &full_bar[stage], ph.w_k0 + g * BK,
+                              n0 + (int)crank * SLICE, wb, kMask);
+          }
         }
       }
     }
@@ -278,7 +318,8 @@ tapgemm_sm100_kernel(const __grid_constant__ TapGemmParams p, const __grid_const
 #pragma unroll
         for (int k = 0; k < BK / 16; ++k)
           umma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (uint32_t)((kb | k) != 0));
-        umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+        if (CS == 1) umma_commit(&empty_bar[stage]);   // frees the smem slot once these MMAs have read it
+        else umma_commit_mcast(&empty_bar[stage], kMask);
       }
       umma_commit(tmem_full_bar);        // accumulator complete
     }
@@ -327,6 +368,7 @@ tapgemm_sm100_kernel(const __grid_constant__ TapGemmParams p, const __grid_const
 
   tcgen05_fence_before();
   __syncthreads();
+  if (CS > 1) cluster_sync_all();   // nobody exits while a peer may still signal or multicast into it
   if (warp == 1) {
     tcgen05_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
@@ -398,19 +440,29 @@ static int encode_bf16_map(CUtensorMap* tm, int rank, const void* base, const cu
   return ITS_OK;
 }
 
-template <int BN, int STAGES, int MIN_CTAS>
+template <int BN, int STAGES, int MIN_CTAS, int CS>
 static int launch_variant(const TapGemmParams& p, const CUtensorMap* tmA, const CUtensorMap& tmB,
                           cudaStream_t stream) {
   using L = SmemLayout<BN, STAGES>;
-  auto kern = tapgemm_sm100_kernel<BN, STAGES, MIN_CTAS>;
+  auto kern = tapgemm_sm100_kernel<BN, STAGES, MIN_CTAS, CS>;
   static bool configured = false;
   if (!configured) {
     ITS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
     configured = true;
   }
-  dim3 grid(p.tiles_x * p.tiles_y * p.tiles_b, (p.Cout + BN - 1) / BN, p.nphases * p.splits);
-  kern<<<grid, NUM_THREADS, L::TOTAL, stream>>>(p, tmA[0], tmA[1], tmA[2], tmB);
-  ITS_CHECK_LAUNCH();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(p.tiles_x * p.tiles_y * p.tiles_b, (p.Cout + BN - 1) / BN, p.nphases * p.splits);
+  cfg.blockDim = dim3(NUM_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = L::TOTAL;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CS;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  ITS_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, p, tmA[0], tmA[1], tmA[2], tmB));
   if (p.splits > 1) {
     const long long items = (long long)p.B * p.Hm * p.Wm * (p.Cout / 8) * p.nphases;
     long long blocks = (items + 255) / 256;
@@ -419,6 +471,14 @@ static int launch_variant(const TapGemmParams& p, const CUtensorMap* tmA, const 
     ITS_CHECK_LAUNCH();
   }
   return ITS_OK;
+}
+
+template <int BN, int STAGES, int MIN_CTAS>
+static int launch_cs(int cs, const TapGemmParams& p, const CUtensorMap* tmA, const CUtensorMap& tmB,
+                     cudaStream_t stream) {
+  if (cs == 4) return launch_variant<BN, STAGES, MIN_CTAS, 4>(p, tmA, tmB, stream);
+  if (cs == 2) return launch_variant<BN, STAGES, MIN_CTAS, 2>(p, tmA, tmB, stream);
+  return launch_variant<BN, STAGES, MIN_CTAS, 1>(p, tmA, tmB, stream);
 }
 
 int tapgemm_launch_sm100(const its_conv_desc* d, const TapGemmParams& p, cudaStream_t stream) {
@@ -439,6 +499,13 @@ int tapgemm_launch_sm100(const its_conv_desc* d, const TapGemmParams& p, cudaStr
   ITS_REQUIRE(p.w_batch_stride == 0 || p.bb == 1, "its_conv_igemm: per-image weights with a multi-image tile");
   ITS_REQUIRE(p.out_nchw || (p.out_c_pitch % 8 == 0 && (p.res == nullptr || p.res_c_pitch % 8 == 0)),
               "its_conv_igemm: out/res pitch alignment");
+
+  // cluster size along M for the weight multicast: consecutive M tiles share the weight tile
+  const int tiles_m = p.tiles_x * p.tiles_y * p.tiles_b;
+  int cs = (d->cluster > 0) ? d->cluster : ((tiles_m % 4 == 0) ? 4 : (tiles_m % 2 == 0) ? 2 : 1);
+  if (p.w_batch_stride != 0) cs = 1;            // per-image B operands are not shared between M tiles
+  ITS_REQUIRE((cs == 1 || cs == 2 || cs == 4) && tiles_m % cs == 0, "its_conv_igemm: cluster=%d does not divide %d M tiles", cs, tiles_m);
+  ITS_REQUIRE(bn % (8 * cs) == 0, "its_conv_igemm: bn=%d not divisible into %d multicast slices", bn, cs);
 
   CUtensorMap tmA[ITS_MAX_SRC];
   memset(tmA, 0, sizeof(tmA));
@@ -470,17 +537,17 @@ int tapgemm_launch_sm100(const its_conv_desc* d, const TapGemmParams& p, cudaStr
     const cuuint64_t strides[2] = {(cuuint64_t)p.w_pitch * 2,
                                    (cuuint64_t)((p.w_batch_stride != 0) ? p.w_batch_stride
                                                                         : (long long)p.Cout * p.w_pitch) * 2};
-    const cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)bn, 1};
+    const cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)(bn / cs), 1};
     const cuuint32_t estr[3] = {1, 1, 1};
     int rc = encode_bf16_map(&tmB, 3, p.w, dims, strides, box, estr, "weights");
     if (rc != ITS_OK) return rc;
   }
   switch (bn) {
-    case 32:  return launch_variant<32, 4, 2>(p, tmA, tmB, stream);
-    case 64:  return launch_variant<64, 4, 2>(p, tmA, tmB, stream);
-    case 128: return launch_variant<128, 3, 2>(p, tmA, tmB, stream);
-    case 192: return launch_variant<192, 5, 1>(p, tmA, tmB, stream);
-    default:  return launch_variant<256, 4, 1>(p, tmA, tmB, stream);
+    case 32:  return launch_cs<32, 4, 2>(cs, p, tmA, tmB, stream);
+    case 64:  return launch_cs<64, 4, 2>(cs, p, tmA, tmB, stream);
+    case 128: return launch_cs<128, 3, 2>(cs, p, tmA, tmB, stream);
+    case 192: return launch_cs<192, 5, 1>(cs, p, tmA, tmB, stream);
+    default:  return launch_cs<256, 4, 1>(cs, p, tmA, tmB, stream);
   }
 }
 

@@ -154,13 +154,25 @@ __global__ void __launch_bounds__(GN_THREADS) gn_cluster_kernel(const GnArgs a) 
 #pragma unroll
   for (int i = 0; i < 8; ++i) sum[i] = sq[i] = 0.f;
   if (pl < prow) {
-    for (int p = p0 + pl; p < p1; p += prow) {
-      const bf16x8 raw = gn_load(a, (long long)img * a.HW + p, cv * 8);
-      if (CACHE) *reinterpret_cast<bf16x8*>(cache + (long long)(p - p0) * a.C + cv * 8) = raw;
-      float f[8];
-      unpack8(raw, f);
+    constexpr int U = 8;   // independent 16-byte loads in flight per thread
+    for (int pb = p0 + pl; pb < p1; pb += prow * U) {
+      bf16x8 raw[U];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) { sum[i] += f[i]; sq[i] = fmaf(f[i], f[i], sq[i]); }
+      for (int u = 0; u < U; ++u) {
+        const int p = pb + u * prow;
+        if (p < p1) raw[u] = gn_load(a, (long long)img * a.HW + p, cv * 8);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int p = pb + u * prow;
+        if (p < p1) {
+          if (CACHE) *reinterpret_cast<bf16x8*>(cache + (long long)(p - p0) * a.C + cv * 8) = raw[u];
+          float f[8];
+          unpack8(raw[u], f);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { sum[i] += f[i]; sq[i] = fmaf(f[i], f[i], sq[i]); }
+        }
+      }
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
