@@ -207,6 +207,8 @@ typedef struct {
   int64_t ws_elems;      /* capacity of ws in floats                     */
   int32_t cluster;       /* CTAs per cluster sharing a multicast weight tile:
                             0 = auto (4/2/1), else 1, 2 or 4             */
+  int64_t* dbg;          /* diagnostics: NULL, or [CTAs][64] clock stamps
+                            (scripts/conv_timeline.py)                   */
 } its_conv_desc;
 
 int its_conv_igemm(const its_conv_desc* desc_host, int32_t impl, void* stream);

@@ -46,7 +46,7 @@ class ConvDesc(C.Structure):
         ("res", C.c_void_p), ("res_c_pitch", C.c_int32), ("res_c_off", C.c_int32),
         ("alpha", C.c_float), ("bn", C.c_int32),
         ("out_nchw", C.c_int32), ("splits", C.c_int32), ("ws", C.c_void_p), ("ws_elems", C.c_int64),
-        ("cluster", C.c_int32),
+        ("cluster", C.c_int32), ("dbg", C.c_void_p),
     ]
 
 

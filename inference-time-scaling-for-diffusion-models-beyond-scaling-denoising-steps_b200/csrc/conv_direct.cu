@@ -208,6 +208,7 @@ int tapgemm_build_params(const its_conv_desc* d, TapGemmParams* p, bool need_k64
   p->out_nchw = d->out_nchw;
   p->splits = d->splits > 1 ? d->splits : 1;
   p->ws = d->ws;
+  p->dbg = reinterpret_cast<long long*>(d->dbg);
   if (p->splits > 1) {
     ITS_REQUIRE(d->ws != nullptr, "its_conv_igemm: splits=%d needs a workspace", d->splits);
     const long long need = (long long)d->nphases * p->splits * d->B * d->Hm * d->Wm * d->Cout;

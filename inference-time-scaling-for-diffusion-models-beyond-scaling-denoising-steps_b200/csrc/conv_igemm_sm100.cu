@@ -234,6 +234,22 @@ tapgemm_sm100_kernel(const __grid_constant__ TapGemmParams p, const __grid_const
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // diagnostics: [0] globaltimer at entry, [1] clock at entry, [2] after setup, [3] producer done
+  // issuing, [4] accumulator complete, [5] epilogue done, [8+kb] clock when k-block kb became full
+  long long* dbg = nullptr;
+  if (p.dbg != nullptr) {
+    const long long cta = blockIdx.x + (long long)gridDim.x * (blockIdx.y + (long long)gridDim.y * blockIdx.z);
+    dbg = p.dbg + cta * 64;
+    if (threadIdx.x == 0) {
+      unsigned long long gt;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+      dbg[0] = (long long)gt;
+      dbg[1] = clock64();
+      unsigned smid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      dbg[6] = smid;
+    }
+  }
   const int phase_idx = blockIdx.z / p.splits, split = blockIdx.z - phase_idx * p.splits;
   const DevPhase& ph = p.phase[phase_idx];
   // split-K: this CTA owns k-blocks [kb0, kb1) of the phase
@@ -266,6 +282,7 @@ tapgemm_sm100_kernel(const __grid_constant__ TapGemmParams p, const __grid_const
   if (CS > 1) cluster_sync_all();   // peers' barriers are initialised before anything remote arrives
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (dbg != nullptr && threadIdx.x == 0) dbg[2] = clock64();
   const uint32_t crank = (CS > 1) ? cluster_ctarank() : 0u;
   constexpr uint16_t kMask = (uint16_t)((1u << CS) - 1u);
 
@@ -302,6 +319,7 @@ tapgemm_sm100_kernel(const __grid_constant__ TapGemmParams p, const __grid_const
           }
         }
       }
+      if (dbg != nullptr) dbg[3] = clock64();
     }
   } else if (warp == 1) {
     // ------------------------------------------------- MMA issuer -----
@@ -312,6 +330,7 @@ tapgemm_sm100_kernel(const __grid_constant__ TapGemmParams p, const __grid_const
         const uint32_t parity = (uint32_t)((kb / STAGES) & 1);
         mbar_wait(&full_bar[stage], parity);
         tcgen05_fence_after();
+        if (dbg != nullptr && kb < 56) dbg[8 + kb] = clock64();
         const uint32_t a_addr = smem_u32(smem + stage * L::STAGE_BYTES);
         const uint64_t adesc = make_smem_desc(a_addr);
         const uint64_t bdesc = make_smem_desc(a_addr + A_BYTES);
@@ -326,35 +345,32 @@ tapgemm_sm100_kernel(const __grid_constant__ TapGemmParams p, const __grid_const
     __syncwarp();
   } else {
     // --------------------------------------------------- epilogue -----
+    // TMEM gives each thread one accumulator ROW; storing rows straight to global would
+    // make every warp store touch 32 different lines (measured: ~4.5 clk per 16-byte
+    // request, a 10 us epilogue).  So: (A) dump the fp32 tile into the now idle pipeline
+    // buffers, (B) re-read it with lanes running along the channel dimension and do
+    // alpha/bias/vectors/residual + the store fully coalesced.
     const int q = warp & 3;              // TMEM lane quarter this warp may access
-    const int row = q * 32 + lane;
-    const int rb = row / (p.bh * p.bw);
-    const int ry = (row / p.bw) % p.bh;
-    const int rx = row % p.bw;
-    const int b = tb * p.bb + rb, y = ty * p.bh + ry, x = tx * p.bw + rx;
-    const bool valid = (b < p.B) && (y < p.Hm) && (x < p.Wm);
-    const long long grow = ((long long)b * p.Hm + y) * p.Wm + x;   // linear GEMM row
-    float* ws_row = nullptr;
-    if (p.splits > 1)
-      ws_row = p.ws + (((long long)blockIdx.z * p.B * p.Hm * p.Wm) + grow) * p.Cout;
-    mbar_wait(tmem_full_bar, 0);
+    const int et = q * 32 + lane;        // epilogue thread id 0..127 (= accumulator row in phase A)
+    constexpr int PITCH = BN + 4;        // fp32 words per staged row (+4: conflict-free float4 access)
+    float* stage_f = reinterpret_cast<float*>(smem);
+    mbar_wait(tmem_full_bar, 0);         // all MMAs done => every TMA load has landed and been consumed
     tcgen05_fence_after();
+    if (dbg != nullptr && warp == 2 && lane == 0) dbg[4] = clock64();
+    if (p.out_nchw) {
+      // thin output (3-channel tail): lanes are consecutive pixels, already coalesced
+      const int rb = et / (p.bh * p.bw), ry = (et / p.bw) % p.bh, rx = et % p.bw;
+      const int b = tb * p.bb + rb, y = ty * p.bh + ry, x = tx * p.bw + rx;
+      const bool valid = (b < p.B) && (y < p.Hm) && (x < p.Wm);
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      uint32_t v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-      if (valid) {
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+        if (valid) {
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const int n = n0 + c0 + g * 8;
-          if (n < p.Cout) {
-            if (ws_row != nullptr) {   // split-K partial: raw accumulators, reduced by the finalize launch
-              float4* dst = reinterpret_cast<float4*>(ws_row + n);
-              dst[0] = make_float4(__uint_as_float(v[g * 8 + 0]), __uint_as_float(v[g * 8 + 1]),
-                                   __uint_as_float(v[g * 8 + 2]), __uint_as_float(v[g * 8 + 3]));
-              dst[1] = make_float4(__uint_as_float(v[g * 8 + 4]), __uint_as_float(v[g * 8 + 5]),
-                                   __uint_as_float(v[g * 8 + 6]), __uint_as_float(v[g * 8 + 7]));
-            } else {
+          for (int g = 0; g < 4; ++g) {
+            const int n = n0 + c0 + g * 8;
+            if (n < p.Cout) {
               float f[8];
 #pragma unroll
               for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[g * 8 + j]);
@@ -363,9 +379,45 @@ tapgemm_sm100_kernel(const __grid_constant__ TapGemmParams p, const __grid_const
           }
         }
       }
+    } else {
+      // (A) accumulator rows -> shared memory
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+        float4* dst = reinterpret_cast<float4*>(stage_f + et * PITCH + c0);
+#pragma unroll
+        for (int g = 0; g < 8; ++g)
+          dst[g] = make_float4(__uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1]),
+                               __uint_as_float(v[4 * g + 2]), __uint_as_float(v[4 * g + 3]));
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");   // the four epilogue warps only
+      // (B) coalesced pass: consecutive threads take consecutive 8-column groups of a row
+      constexpr int NCG = BN / 8;
+      const long long rows_total = (long long)p.B * p.Hm * p.Wm;
+#pragma unroll 1
+      for (int i = et; i < BM * NCG; i += 128) {
+        const int r = i / NCG, cgi = i - r * NCG;
+        const int n = n0 + cgi * 8;
+        const int rb = r / (p.bh * p.bw), ry = (r / p.bw) % p.bh, rx = r % p.bw;
+        const int b = tb * p.bb + rb, y = ty * p.bh + ry, x = tx * p.bw + rx;
+        if (b >= p.B || y >= p.Hm || x >= p.Wm || n >= p.Cout) continue;
+        const float4* src = reinterpret_cast<const float4*>(stage_f + r * PITCH + cgi * 8);
+        const float4 lo = src[0], hi = src[1];
+        float f[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+        if (p.splits > 1) {   // split-K partial: raw accumulators, reduced by the finalize launch
+          const long long grow = ((long long)b * p.Hm + y) * p.Wm + x;
+          float4* dst = reinterpret_cast<float4*>(p.ws + ((long long)blockIdx.z * rows_total + grow) * p.Cout + n);
+          dst[0] = lo;
+          dst[1] = hi;
+        } else {
+          apply_and_store8(p, ph, b, y, x, n, f);
+        }
+      }
     }
   }
 
+  if (dbg != nullptr && warp == 2 && lane == 0) dbg[5] = clock64();
   tcgen05_fence_before();
   __syncthreads();
   if (CS > 1) cluster_sync_all();   // nobody exits while a peer may still signal or multicast into it
@@ -502,7 +554,9 @@ int tapgemm_launch_sm100(const its_conv_desc* d, const TapGemmParams& p, cudaStr
 
   // cluster size along M for the weight multicast: consecutive M tiles share the weight tile
   const int tiles_m = p.tiles_x * p.tiles_y * p.tiles_b;
-  int cs = (d->cluster > 0) ? d->cluster : ((tiles_m % 4 == 0) ? 4 : (tiles_m % 2 == 0) ? 2 : 1);
+  // measured (scripts/conv_timeline.py): the mainloop already runs at the MMA rate with unicast
+  // weights, and a cluster launch costs ~0.4 us of setup, so multicast is opt-in
+  int cs = (d->cluster > 0) ? d->cluster : 1;
   if (p.w_batch_stride != 0) cs = 1;            // per-image B operands are not shared between M tiles
   ITS_REQUIRE((cs == 1 || cs == 2 || cs == 4) && tiles_m % cs == 0, "its_conv_igemm: cluster=%d does not divide %d M tiles", cs, tiles_m);
   ITS_REQUIRE(bn % (8 * cs) == 0, "its_conv_igemm: bn=%d not divisible into %d multicast slices", bn, cs);

@@ -38,6 +38,7 @@ struct TapGemmParams {
   int out_nchw;
   int splits;                // split-K factor (>= 1)
   float* ws;                 // [nphases][splits][B*Hm*Wm][Cout] fp32 partial sums
+  long long* dbg;            // optional per-CTA clock stamps (diagnostics)
   // M tiling: a 128-row tile is a (bb images) x (bh rows) x (bw cols) box
   int bw, bh, bb, tiles_x, tiles_y, tiles_b;
 };
