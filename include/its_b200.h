@@ -43,6 +43,8 @@ extern "C" {
 int its_version(void);                     /* 10000*major + 100*minor + patch */
 const char* its_last_error_string(void);   /* per-thread, never NULL          */
 int its_device_sm_count(int* out_host);    /* cudaDevAttrMultiProcessorCount  */
+int its_set_pdl(int32_t enabled);         /* programmatic dependent launch on
+                                              every kernel (default 1; env ITS_PDL) */
 int its_abi_sizeof(int which);             /* 0: its_conv_desc, 1: its_src_t,
                                               2: its_phase_t (binding self-check) */
 
@@ -113,6 +115,10 @@ int its_linear(float* y, const float* x, const float* W, const float* bias,
  * GroupNorm(32 groups) [+ Swish] over the channel concatenation of up to two
  * NHWC bf16 tensors, written as one NHWC bf16 tensor of C0+C1 channels
  * (Model.py:170-173,186-190,132,257-259 and the skip concat Model.py:279-280).
+ * With stats0 (and stats1 when src1 is given) the statistics are not recomputed:
+ * they are reduced, in a fixed order and in double precision, from the partial
+ * sums the producing tap-GEMM wrote (its_conv_desc.stats), and the launch is one
+ * streaming normalise+Swish pass (its_group_norm_apply).
  * Deterministic (no float atomics).  chunks <= 8: ONE launch, the chunks of an
  * image form a thread-block cluster and exchange partial sums through distributed
  * shared memory; chunks > 8: two launches through `partials`, scratch of
@@ -123,6 +129,13 @@ int its_group_norm(void* out, const void* src0, int32_t C0, const void* src1,
                    int32_t n_img, int32_t HW, int32_t groups, float eps,
                    int32_t silu, float* partials, int32_t chunks,
                    void* stream);
+
+int its_group_norm_apply(void* out, const void* src0, int32_t C0,
+                         const float* stats0, int32_t parts0, const void* src1,
+                         int32_t C1, const float* stats1, int32_t parts1,
+                         const float* gamma, const float* beta, int32_t n_img,
+                         int32_t HW, int32_t groups, float eps, int32_t silu,
+                         void* stream);
 
 /* ------------------------------------------------------------------------
  * Head / tail convolutions (CUDA-core special cases, fp32 weights).
@@ -209,9 +222,20 @@ typedef struct {
                             0 = auto (4/2/1), else 1, 2 or 4             */
   int64_t* dbg;          /* diagnostics: NULL, or [CTAs][64] clock stamps
                             (scripts/conv_timeline.py)                   */
+  float* stats;          /* out, optional: GroupNorm partial sums of the
+                            stored bf16 tensor, [B][stats_parts][Cout/4]
+                            {sum, sum of squares} (persistent schedule)   */
+  int32_t stats_parts;   /* its_conv_stats_parts() of this descriptor     */
+  int32_t schedule;      /* 0 = auto, 1 = one tile per CTA, 2 = persistent
+                            CTAs (TMEM double buffer, TMA-store epilogue) */
 } its_conv_desc;
 
 int its_conv_igemm(const its_conv_desc* desc_host, int32_t impl, void* stream);
+
+/* Number of partial-sum slots per image the persistent schedule writes into
+ * desc->stats for this descriptor's tiling, or 0 when the layer cannot run on
+ * the persistent schedule (no statistics are produced then).               */
+int its_conv_stats_parts(const its_conv_desc* desc_host);
 
 /* ------------------------------------------------------------------------
  * Attention pieces (Model.py:153-158): row softmax of fp32 scores -> bf16

@@ -18,6 +18,7 @@ SYMBOLS = [
     "its_philox_normal", "its_step_advance", "its_time_embed", "its_embed_rows", "its_linear",
     "its_group_norm", "its_conv_head", "its_conv_tail", "its_conv_igemm", "its_softmax_rows",
     "its_attention_small", "its_image_stats", "its_candidate_scores", "its_argmax_first",
+    "its_group_norm_apply", "its_conv_stats_parts", "its_set_pdl",
 ]
 
 
@@ -47,6 +48,7 @@ class ConvDesc(C.Structure):
         ("alpha", C.c_float), ("bn", C.c_int32),
         ("out_nchw", C.c_int32), ("splits", C.c_int32), ("ws", C.c_void_p), ("ws_elems", C.c_int64),
         ("cluster", C.c_int32), ("dbg", C.c_void_p),
+        ("stats", C.c_void_p), ("stats_parts", C.c_int32), ("schedule", C.c_int32),
     ]
 
 
@@ -71,6 +73,7 @@ def lib() -> C.CDLL:
     L.its_last_error_string.restype = C.c_char_p
     L.its_device_sm_count.argtypes = [C.POINTER(C.c_int)]
     L.its_abi_sizeof.argtypes = [i32]
+    L.its_set_pdl.argtypes = [i32]
     L.its_ddpm_step.argtypes = [vp, vp, vp, vp, i64, i64, i64, vp, vp, f64, u64, i64, vp, i32, vp]
     L.its_philox_normal.argtypes = [vp, vp, i32, f32, i64, i64, u64, i64, i32, vp]
     L.its_step_advance.argtypes = [vp, i32, vp]
@@ -78,6 +81,8 @@ def lib() -> C.CDLL:
     L.its_embed_rows.argtypes = [vp, vp, vp, vp, i32, i32, i32, vp]
     L.its_linear.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]
     L.its_group_norm.argtypes = [vp, vp, i32, vp, i32, vp, vp, i32, i32, i32, f32, i32, vp, i32, vp]
+    L.its_group_norm_apply.argtypes = [vp, vp, i32, vp, i32, vp, i32, vp, i32, vp, vp, i32, i32, i32, f32, i32, vp]
+    L.its_conv_stats_parts.argtypes = [C.POINTER(ConvDesc)]
     L.its_conv_head.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]
     L.its_conv_tail.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]
     L.its_conv_igemm.argtypes = [C.POINTER(ConvDesc), i32, vp]

@@ -9,6 +9,7 @@ namespace its {
 __global__ void __launch_bounds__(256) softmax_rows_kernel(__nv_bfloat16* __restrict__ probs,
                                                            const float* __restrict__ scores,
                                                            long long n_rows, int n_cols) {
+  pdl_prologue();
   const long long row = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= n_rows) return;
@@ -29,6 +30,7 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(__nv_bfloat16* __rest
 __global__ void __launch_bounds__(256) attention_small_kernel(__nv_bfloat16* __restrict__ out,
                                                               const __nv_bfloat16* __restrict__ qkv,
                                                               int N, int C, float scale) {
+  pdl_prologue();
   __shared__ float s_p[64];
   const int img = blockIdx.y, qi = blockIdx.x;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -81,7 +83,7 @@ extern "C" int its_softmax_rows(void* probs_bf16, const float* scores, int64_t n
   ITS_REQUIRE(probs_bf16 && scores && n_rows > 0 && n_cols > 0, "its_softmax_rows: bad arguments");
   const long long blocks = (n_rows * 32 + 255) / 256;
   ITS_REQUIRE(blocks < (1LL << 31), "its_softmax_rows: too many rows");
-  its::softmax_rows_kernel<<<(unsigned)blocks, 256, 0, its::as_stream(stream)>>>(
+  ITS_LAUNCH(its::softmax_rows_kernel, dim3((unsigned)blocks), dim3(256), 0, its::as_stream(stream), 
       static_cast<__nv_bfloat16*>(probs_bf16), scores, n_rows, n_cols);
   ITS_CHECK_LAUNCH();
   return ITS_OK;
@@ -93,7 +95,7 @@ extern "C" int its_attention_small(void* out, const void* qkv, int32_t n_img, in
   ITS_REQUIRE(n_img > 0 && n_img <= 65535 && N > 0 && N <= 64 && C > 0 && C % 8 == 0,
               "its_attention_small: unsupported N=%d C=%d n_img=%d", N, C, n_img);
   dim3 grid(N, n_img);
-  its::attention_small_kernel<<<grid, 256, 0, its::as_stream(stream)>>>(
+  ITS_LAUNCH(its::attention_small_kernel, dim3(grid), dim3(256), 0, its::as_stream(stream), 
       static_cast<__nv_bfloat16*>(out), static_cast<const __nv_bfloat16*>(qkv), N, C, scale);
   ITS_CHECK_LAUNCH();
   return ITS_OK;

@@ -15,6 +15,7 @@ template <int CIN>
 __global__ void __launch_bounds__(256) conv_head_kernel(
     __nv_bfloat16* __restrict__ out, const float* __restrict__ x, const float* __restrict__ W,
     const float* __restrict__ bias, int n_img, int n_img_in, int H, int Wd, int Cout) {
+  pdl_prologue();
   extern __shared__ float s_w[];  // [CIN*9][Cout] then bias[Cout]
   constexpr int K = CIN * 9;
   for (int i = threadIdx.x; i < K * Cout; i += blockDim.x) {
@@ -72,6 +73,7 @@ __global__ void __launch_bounds__(256) conv_head_kernel(
 __global__ void __launch_bounds__(256) conv_tail_kernel(
     float* __restrict__ out, const __nv_bfloat16* __restrict__ act, const float* __restrict__ W,
     const float* __restrict__ bias, int n_img, int H, int Wd, int Cin, int Cout) {
+  pdl_prologue();
   extern __shared__ float s_w[];  // [9][Cin][4]
   for (int i = threadIdx.x; i < 9 * Cin * 4; i += blockDim.x) {
     const int co = i & 3, ci = (i >> 2) % Cin, tap = (i >> 2) / Cin;
@@ -115,6 +117,7 @@ __global__ void __launch_bounds__(256) conv_tail_kernel(
 // One thread per (GEMM row, output column); same parameter block, packed
 // weights and epilogue as the tcgen05 kernel.
 __global__ void __launch_bounds__(128) tapgemm_ref_kernel(const TapGemmParams p) {
+  pdl_prologue();
   const int n = blockIdx.y * blockDim.x + threadIdx.x;
   const long long row = blockIdx.x;
   const DevPhase& ph = p.phase[blockIdx.z];
@@ -156,7 +159,7 @@ int tapgemm_launch_ref(const TapGemmParams& p, cudaStream_t stream) {
   const long long rows = (long long)p.B * p.Hm * p.Wm;
   ITS_REQUIRE(rows <= 2147483647LL, "tapgemm_ref: too many rows");
   dim3 grid((unsigned)rows, (p.Cout + 127) / 128, p.nphases);
-  tapgemm_ref_kernel<<<grid, 128, 0, stream>>>(p);
+  ITS_LAUNCH(tapgemm_ref_kernel, dim3(grid), dim3(128), 0, stream, p);
   ITS_CHECK_LAUNCH();
   return ITS_OK;
 }
@@ -209,6 +212,8 @@ int tapgemm_build_params(const its_conv_desc* d, TapGemmParams* p, bool need_k64
   p->splits = d->splits > 1 ? d->splits : 1;
   p->ws = d->ws;
   p->dbg = reinterpret_cast<long long*>(d->dbg);
+  p->stats = d->stats;
+  p->stats_parts = d->stats_parts;
   if (p->splits > 1) {
     ITS_REQUIRE(d->ws != nullptr, "its_conv_igemm: splits=%d needs a workspace", d->splits);
     const long long need = (long long)d->nphases * p->splits * d->B * d->Hm * d->Wm * d->Cout;
@@ -257,7 +262,7 @@ extern "C" int its_conv_head(void* out, const float* x, const float* W, const fl
   const long long npix = (long long)n_img * H * Wd;
   long long blocks = (npix + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
-  conv_head_kernel<3><<<(unsigned)blocks, 256, smem, as_stream(stream)>>>(
+  ITS_LAUNCH(conv_head_kernel<3>, dim3((unsigned)blocks), dim3(256), smem, as_stream(stream), 
       static_cast<__nv_bfloat16*>(out), x, W, bias, n_img, n_img_in, H, Wd, Cout);
   ITS_CHECK_LAUNCH();
   return ITS_OK;
@@ -275,7 +280,7 @@ extern "C" int its_conv_tail(float* out, const void* act, const float* W, const 
   const long long npix = (long long)n_img * H * Wd;
   long long blocks = (npix * 32 + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
-  conv_tail_kernel<<<(unsigned)blocks, 256, smem, as_stream(stream)>>>(
+  ITS_LAUNCH(conv_tail_kernel, dim3((unsigned)blocks), dim3(256), smem, as_stream(stream), 
       out, static_cast<const __nv_bfloat16*>(act), W, bias, n_img, H, Wd, Cin, Cout);
   ITS_CHECK_LAUNCH();
   return ITS_OK;
@@ -286,7 +291,23 @@ extern "C" int its_conv_igemm(const its_conv_desc* desc_host, int32_t impl, void
   TapGemmParams p;
   int rc = tapgemm_build_params(desc_host, &p, impl == 0);
   if (rc != ITS_OK) return rc;
-  if (impl == 1) return tapgemm_launch_ref(p, as_stream(stream));
+  ITS_REQUIRE(desc_host->schedule >= 0 && desc_host->schedule <= 2, "its_conv_igemm: schedule=%d", desc_host->schedule);
+  if (impl == 1) {
+    ITS_REQUIRE(p.stats == nullptr, "its_conv_igemm: GroupNorm statistics need the persistent tcgen05 schedule");
+    return tapgemm_launch_ref(p, as_stream(stream));
+  }
   ITS_REQUIRE(impl == 0, "its_conv_igemm: impl=%d", impl);
+  const bool persist = desc_host->schedule != 1 && tapgemm_persist_eligible(desc_host, p);
+  ITS_REQUIRE(persist || desc_host->schedule != 2, "its_conv_igemm: schedule=2 but the layer is not eligible for the persistent kernel");
+  if (persist) return tapgemm_launch_persist(desc_host, p, as_stream(stream));
+  ITS_REQUIRE(p.stats == nullptr, "its_conv_igemm: GroupNorm statistics need the persistent tcgen05 schedule");
   return tapgemm_launch_sm100(desc_host, p, as_stream(stream));
+}
+
+extern "C" int its_conv_stats_parts(const its_conv_desc* desc_host) {
+  using namespace its;
+  TapGemmParams p;
+  if (tapgemm_build_params(desc_host, &p, true) != ITS_OK) return 0;
+  if (desc_host->schedule == 1 || !tapgemm_persist_eligible(desc_host, p)) return 0;
+  return tapgemm_stats_parts(p);
 }

@@ -22,141 +22,9 @@
 //
 // Reference semantics: see its_conv_igemm in include/its_b200.h.
 #include "tapgemm.cuh"
-#include <cuda.h>  // CUtensorMap (types only; the encoder is fetched at run time)
+#include "sm100_ptx.cuh"
 
 namespace its {
-
-constexpr int BM = 128;
-constexpr int BK = 64;
-constexpr int A_BYTES = BM * BK * 2;
-constexpr int NUM_THREADS = 192;
-constexpr uint32_t SPIN_LIMIT = 1u << 20;  // bounded waits: trap instead of hanging the GPU
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
-}
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  const uint32_t addr = smem_u32(bar);
-  uint32_t ok = 0;
-#pragma unroll 1
-  for (uint32_t spin = 0; spin < SPIN_LIMIT; ++spin) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t"
-        "}"
-        : "=r"(ok)
-        : "r"(addr), "r"(parity)
-        : "memory");
-    if (ok) return;
-  }
-  __trap();  // a lost arrival would otherwise hang the device
-}
-__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0,
-                                            int c1, int c2, int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes"
-      " [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1),
-        "r"(c2), "r"(c3)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0,
-                                            int c1, int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes"
-      " [%0], [%1, {%3, %4, %5}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1),
-        "r"(c2)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_3d_mcast(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0,
-                                                  int c1, int c2, uint16_t cta_mask) {
-  // the box lands at the same CTA-relative offset in every CTA of cta_mask and
-  // completes bytes on the mbarrier at the same offset in each of them
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
-      " [%0], [%1, {%3, %4, %5}], [%2], %6;"
-      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1),
-        "r"(c2), "h"(cta_mask)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit_mcast(uint64_t* bar, uint16_t cta_mask) {
-  asm volatile(
-      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-      ::"r"(smem_u32(bar)), "h"(cta_mask)
-      : "memory");
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void tcgen05_fence_after() {
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-}
-__device__ __forceinline__ void tcgen05_fence_before() {
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-}
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
-                                          uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-      "}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
-                   smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),
-        "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]),
-        "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]),
-        "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 "version 1"):
-// rows of 128 bytes, 8-row swizzle atoms 1024 bytes apart.
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr >> 4) & 0x3FFFu);       // start address, 16-byte units
-  d |= (uint64_t)1 << 16;                        // leading byte offset (ignored for SW128 K-major)
-  d |= (uint64_t)(1024 >> 4) << 32;              // stride byte offset between 8-row groups
-  d |= (uint64_t)1 << 46;                        // descriptor version (Blackwell)
-  d |= (uint64_t)2 << 61;                        // layout type: SWIZZLE_128B
-  return d;
-}
-// Instruction descriptor: D fp32, A/B bf16, both K-major, M=128, N=BN.
-__host__ __device__ constexpr uint32_t make_idesc(int bn) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-}
-
-__host__ __device__ constexpr int tmem_cols_for(int bn) { return bn <= 32 ? 32 : bn <= 64 ? 64 : bn <= 128 ? 128 : 256; }
 
 // alpha / bias / per-image vectors / residual, then the store in one of the three
 // output formats.  f[8] holds raw accumulators of columns n..n+7 of GEMM row (b,y,x).
@@ -282,6 +150,7 @@ tapgemm_sm100_kernel(const __grid_constant__ TapGemmParams p, const __grid_const
   if (CS > 1) cluster_sync_all();   // peers' barriers are initialised before anything remote arrives
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_prologue();   // set-up above overlaps the previous kernel's tail; global memory only from here on
   if (dbg != nullptr && threadIdx.x == 0) dbg[2] = clock64();
   const uint32_t crank = (CS > 1) ? cluster_ctarank() : 0u;
   constexpr uint16_t kMask = (uint16_t)((1u << CS) - 1u);
@@ -432,6 +301,7 @@ tapgemm_sm100_kernel(const __grid_constant__ TapGemmParams p, const __grid_const
 // Split-K second pass: sum the `splits` partial tiles in a fixed order, then the
 // same epilogue.  One thread per (phase, GEMM row, 8 output columns).
 __global__ void __launch_bounds__(256) tapgemm_finalize_kernel(const TapGemmParams p) {
+  pdl_prologue();
   const int nv = p.Cout / 8;
   const long long rows = (long long)p.B * p.Hm * p.Wm;
   const long long total = rows * nv * p.nphases;
@@ -476,7 +346,7 @@ static EncodeTiledFn get_encoder() {
   return fn;
 }
 
-static int encode_bf16_map(CUtensorMap* tm, int rank, const void* base, const cuuint64_t* dims,
+int encode_bf16_map(CUtensorMap* tm, int rank, const void* base, const cuuint64_t* dims,
                            const cuuint64_t* strides_bytes, const cuuint32_t* box,
                            const cuuint32_t* estr, const char* what) {
   EncodeTiledFn enc = get_encoder();
@@ -489,6 +359,47 @@ static int encode_bf16_map(CUtensorMap* tm, int rank, const void* base, const cu
                      "cuTensorMapEncodeTiled(%s) failed: CUresult %d (rank %d dims %llu,%llu,%llu box %u,%u,%u)",
                      what, (int)r, rank, (unsigned long long)dims[0], (unsigned long long)dims[1],
                      (unsigned long long)dims[2], box[0], box[1], box[2]);
+  return ITS_OK;
+}
+
+// Tensor maps of the A sources (4-D boxes of bb x bh x bw pixels x 64 channels) and of the
+// packed weights (3-D: K, Cout, per-image batch; box 64 x b_box_rows x 1).
+int tapgemm_encode_operand_maps(const TapGemmParams& p, int b_box_rows, CUtensorMap* tmA, CUtensorMap* tmB_out,
+                                int row_boxes) {
+  memset(tmA, 0, sizeof(CUtensorMap) * ITS_MAX_SRC);
+  for (int s = 0; s < p.nsrc; ++s) {
+    const DevSrc& in = p.src[s];
+    ITS_REQUIRE((reinterpret_cast<uintptr_t>(in.ptr) & 15) == 0, "its_conv_igemm: src %d pointer alignment", s);
+    ITS_REQUIRE(p.bw * in.stride <= 256 && p.bh * row_boxes * in.stride <= 256, "its_conv_igemm: box too large");
+    const cuuint64_t dims[4] = {(cuuint64_t)in.C, (cuuint64_t)in.W, (cuuint64_t)in.H,
+                                (cuuint64_t)(in.bcast ? 1 : p.B)};
+    const cuuint64_t strides[3] = {(cuuint64_t)in.c_pitch * 2, (cuuint64_t)in.W * in.c_pitch * 2,
+                                   (cuuint64_t)in.H * in.W * in.c_pitch * 2};
+    const cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)(p.bw * in.stride), (cuuint32_t)(p.bh * row_boxes * in.stride),
+                               (cuuint32_t)p.bb};
+    const cuuint32_t estr[4] = {1, (cuuint32_t)in.stride, (cuuint32_t)in.stride, 1};
+    int rc = encode_bf16_map(&tmA[s], 4, in.ptr, dims, strides, box, estr, "activations");
+    if (rc != ITS_OK) return rc;
+  }
+  for (int s = p.nsrc; s < ITS_MAX_SRC; ++s) tmA[s] = tmA[0];
+
+  int k_extent = 0;
+  for (int f = 0; f < p.nphases; ++f) {
+    const int k1 = p.phase[f].w_k0 + p.phase[f].nkb * BK;
+    if (k1 > k_extent) k_extent = k1;
+  }
+  CUtensorMap& tmB = *tmB_out;
+  {
+    const long long nbatch = (p.w_batch_stride != 0) ? p.B : 1;
+    const cuuint64_t dims[3] = {(cuuint64_t)k_extent, (cuuint64_t)p.Cout, (cuuint64_t)nbatch};
+    const cuuint64_t strides[2] = {(cuuint64_t)p.w_pitch * 2,
+                                   (cuuint64_t)((p.w_batch_stride != 0) ? p.w_batch_stride
+                                                                        : (long long)p.Cout * p.w_pitch) * 2};
+    const cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)b_box_rows, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    int rc = encode_bf16_map(&tmB, 3, p.w, dims, strides, box, estr, "weights");
+    if (rc != ITS_OK) return rc;
+  }
   return ITS_OK;
 }
 
@@ -507,19 +418,21 @@ static int launch_variant(const TapGemmParams& p, const CUtensorMap* tmA, const 
   cfg.blockDim = dim3(NUM_THREADS, 1, 1);
   cfg.dynamicSmemBytes = L::TOTAL;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CS;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   ITS_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, p, tmA[0], tmA[1], tmA[2], tmB));
   if (p.splits > 1) {
     const long long items = (long long)p.B * p.Hm * p.Wm * (p.Cout / 8) * p.nphases;
     long long blocks = (items + 255) / 256;
     if (blocks > 148 * 8) blocks = 148 * 8;
-    tapgemm_finalize_kernel<<<(unsigned)blocks, 256, 0, stream>>>(p);
+    ITS_LAUNCH(tapgemm_finalize_kernel, dim3((unsigned)blocks), dim3(256), 0, stream, p);
     ITS_CHECK_LAUNCH();
   }
   return ITS_OK;
@@ -561,39 +474,9 @@ int tapgemm_launch_sm100(const its_conv_desc* d, const TapGemmParams& p, cudaStr
   ITS_REQUIRE((cs == 1 || cs == 2 || cs == 4) && tiles_m % cs == 0, "its_conv_igemm: cluster=%d does not divide %d M tiles", cs, tiles_m);
   ITS_REQUIRE(bn % (8 * cs) == 0, "its_conv_igemm: bn=%d not divisible into %d multicast slices", bn, cs);
 
-  CUtensorMap tmA[ITS_MAX_SRC];
-  memset(tmA, 0, sizeof(tmA));
-  for (int s = 0; s < p.nsrc; ++s) {
-    const DevSrc& in = p.src[s];
-    ITS_REQUIRE((reinterpret_cast<uintptr_t>(in.ptr) & 15) == 0, "its_conv_igemm: src %d pointer alignment", s);
-    ITS_REQUIRE(p.bw * in.stride <= 256 && p.bh * in.stride <= 256, "its_conv_igemm: box too large");
-    const cuuint64_t dims[4] = {(cuuint64_t)in.C, (cuuint64_t)in.W, (cuuint64_t)in.H,
-                                (cuuint64_t)(in.bcast ? 1 : p.B)};
-    const cuuint64_t strides[3] = {(cuuint64_t)in.c_pitch * 2, (cuuint64_t)in.W * in.c_pitch * 2,
-                                   (cuuint64_t)in.H * in.W * in.c_pitch * 2};
-    const cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)(p.bw * in.stride), (cuuint32_t)(p.bh * in.stride),
-                               (cuuint32_t)p.bb};
-    const cuuint32_t estr[4] = {1, (cuuint32_t)in.stride, (cuuint32_t)in.stride, 1};
-    int rc = encode_bf16_map(&tmA[s], 4, in.ptr, dims, strides, box, estr, "activations");
-    if (rc != ITS_OK) return rc;
-  }
-  for (int s = p.nsrc; s < ITS_MAX_SRC; ++s) tmA[s] = tmA[0];
-
-  int k_extent = 0;
-  for (int f = 0; f < p.nphases; ++f) {
-    const int k1 = p.phase[f].w_k0 + p.phase[f].nkb * BK;
-    if (k1 > k_extent) k_extent = k1;
-  }
-  CUtensorMap tmB;
+  CUtensorMap tmA[ITS_MAX_SRC], tmB;
   {
-    const long long nbatch = (p.w_batch_stride != 0) ? p.B : 1;
-    const cuuint64_t dims[3] = {(cuuint64_t)k_extent, (cuuint64_t)p.Cout, (cuuint64_t)nbatch};
-    const cuuint64_t strides[2] = {(cuuint64_t)p.w_pitch * 2,
-                                   (cuuint64_t)((p.w_batch_stride != 0) ? p.w_batch_stride
-                                                                        : (long long)p.Cout * p.w_pitch) * 2};
-    const cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)(bn / cs), 1};
-    const cuuint32_t estr[3] = {1, 1, 1};
-    int rc = encode_bf16_map(&tmB, 3, p.w, dims, strides, box, estr, "weights");
+    int rc = tapgemm_encode_operand_maps(p, bn / cs, tmA, &tmB, 1);
     if (rc != ITS_OK) return rc;
   }
   switch (bn) {

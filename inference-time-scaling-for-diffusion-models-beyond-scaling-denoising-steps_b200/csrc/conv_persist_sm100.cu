@@ -1,0 +1,486 @@
+// Persistent tap-GEMM (implicit-GEMM convolution) for sm_100a.
+//
+// Same maths and operand layout as conv_igemm_sm100.cu (see its_conv_igemm in
+// include/its_b200.h), different schedule:
+//
+// * one CTA per SM walks a static list of output tiles (phase, N tile, M tile), so the
+//   barrier/TMEM set-up and the first TMA round trip are paid once per CTA, not per tile;
+// * the fp32 accumulator is double buffered in TMEM (2 x BN columns): while the four
+//   epilogue warps drain tile j, the MMA warp already accumulates tile j+1 into the other
+//   buffer, fed by the same shared-memory ring;
+// * the epilogue works on 64-column panels: tcgen05.ld -> alpha/bias/per-image vectors ->
+//   bf16 -> 128B-swizzled shared memory -> one TMA tensor store per panel (two panel
+//   buffers, bulk-group completion), so no thread issues an uncoalesced global store;
+// * GroupNorm statistics of the tensor being written are a by-product: column sums and
+//   sums of squares of the bf16 values in the staged panel, per (image, 4 channels, tile),
+//   written to a small partial-sum array that the GroupNorm-apply kernel of the consuming
+//   layer reduces in a fixed order (Model.py:170,186: GroupNorm(32, C) reads exactly the
+//   tensor this kernel stores).
+//
+// Restrictions (the launcher falls back to the one-tile-per-CTA kernel otherwise):
+// bf16 NHWC output, weights shared by all images, no split-K, no residual pointer (the
+// identity shortcut is appended as an extra K block with identity weights by the caller),
+// Cout a multiple of 64.
+#include "tapgemm.cuh"
+#include "sm100_ptx.cuh"
+
+namespace its {
+
+constexpr int P_THREADS = 352;       // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue, warp 10 TMA stores
+constexpr int P_EPI_THREADS = 256;
+constexpr int PANEL_COLS = 64;
+constexpr int PANEL_BYTES = BM * PANEL_COLS * 2;   // 128 rows x 128 bytes
+
+// MT = 128-row sub-tiles (accumulators) per tile: MT = 2 shares every weight tile between two
+// vertically adjacent row boxes, halving the weight traffic per MMA.
+template <int BN, int STAGES, int MT>
+struct PersistSmem {
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = MT * A_BYTES + B_BYTES;
+  static constexpr int STAGING_OFF = STAGES * STAGE_BYTES;          // 2 panel buffers
+  static constexpr int RED_OFF = STAGING_OFF + 2 * PANEL_BYTES;     // [8 sub-blocks][16 chunks] float2
+  static constexpr int RED_BYTES = 2 * 8 * 16 * 8;   // double buffered
+  static constexpr int BAR_OFF = RED_OFF + RED_BYTES;
+  static constexpr int NBARS = 2 * STAGES + 8;
+  static constexpr int TOTAL = BAR_OFF + NBARS * 8 + 16;            // no slack: the window is 1024-aligned
+  static constexpr int TMEM_COLS = (2 * MT * BN <= 128) ? 128 : (2 * MT * BN <= 256) ? 256 : 512;
+  static_assert(2 * MT * BN <= 512, "TMEM holds two accumulator sets");
+};
+
+struct TileCoord {
+  int phase, n0, tx, ty, tb;
+};
+
+// ty counts tiles of mt row boxes (p.tiles_y counts 128-row boxes)
+__device__ __forceinline__ TileCoord decode_tile(const TapGemmParams& p, int tile, int tiles_m, int tiles_n,
+                                                  int bn, int mt_per_tile) {
+  TileCoord c;
+  const int tpp = tiles_m * tiles_n;
+  c.phase = tile / tpp;
+  const int r = tile - c.phase * tpp;
+  const int nt = r / tiles_m;
+  const int mt = r - nt * tiles_m;
+  c.n0 = nt * bn;
+  const int ty_tiles = p.tiles_y / mt_per_tile;
+  c.tx = mt % p.tiles_x;
+  c.ty = (mt / p.tiles_x) % ty_tiles;
+  c.tb = mt / (p.tiles_x * ty_tiles);
+  return c;
+}
+
+template <int BN, int STAGES, int MT>
+__global__ void __launch_bounds__(P_THREADS, 1)
+tapgemm_persist_kernel(const __grid_constant__ TapGemmParams p, const __grid_constant__ CUtensorMap tmA0,
+                       const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
+                       const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut) {
+  using L = PersistSmem<BN, STAGES, MT>;
+  // SWIZZLE_128B atoms need 1024-byte alignment; with no static shared memory the dynamic
+  // window starts 1024-aligned (checked: a misaligned window traps instead of corrupting)
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0u) __trap();
+  uint8_t* staging = smem + L::STAGING_OFF;
+  float2* red = reinterpret_cast<float2*>(smem + L::RED_OFF);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;     // [2] accumulator buffer complete
+  uint64_t* tempty_bar = tfull_bar + 2;         // [2] accumulator buffer drained
+  uint64_t* pfull_bar = tempty_bar + 2;         // [2] staged output panel complete
+  uint64_t* pempty_bar = pfull_bar + 2;         // [2] staged output panel stored
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_m = p.tiles_x * (p.tiles_y / MT) * p.tiles_b;
+  const int tiles_n = (p.Cout + BN - 1) / BN;
+  const int total_tiles = tiles_m * tiles_n * p.nphases;
+
+  long long* dbg = nullptr;
+  if (p.dbg != nullptr) {
+    dbg = p.dbg + (long long)blockIdx.x * 64;
+    if (threadIdx.x == 0) {
+      unsigned long long gt;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+      dbg[0] = (long long)gt;
+      dbg[1] = clock64();
+      unsigned smid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      dbg[6] = smid;
+    }
+  }
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tfull_bar[b], 1);
+      mbar_init(&tempty_bar[b], P_EPI_THREADS);
+      mbar_init(&pfull_bar[b], P_EPI_THREADS);
+      mbar_init(&pempty_bar[b], 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    tma_prefetch_desc(&tmA0);
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmOut);
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)L::TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  // everything above overlaps the tail of the previous kernel under programmatic dependent
+  // launch; nothing below may touch global memory before the producer grid has finished
+  pdl_prologue();
+  if (dbg != nullptr && threadIdx.x == 0) dbg[2] = clock64();
+
+  if (warp == 0) {
+    // ------------------------------------------------ TMA producer ----
+    if (lane == 0) {
+      uint32_t it = 0;   // k-blocks issued so far (ring position)
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const TileCoord c = decode_tile(p, tile, tiles_m, tiles_n, BN, MT);
+        const DevPhase& ph = p.phase[c.phase];
+        int g = 0;
+        for (int t = 0; t < ph.ntaps; ++t) {
+          const int si = ph.src[t];
+          const DevSrc& s = p.src[si];
+          const int ncb = s.C / BK;
+          const CUtensorMap* tm = (si == 0) ? &tmA0 : (si == 1) ? &tmA1 : &tmA2;
+          const int cx = c.tx * p.bw * s.stride + ph.dx[t];
+          const int cy = c.ty * (p.bh * MT) * s.stride + ph.dy[t];
+          const int cb_img = s.bcast ? 0 : c.tb * p.bb;
+          for (int cb = 0; cb < ncb; ++cb, ++g, ++it) {
+            const uint32_t stage = it % STAGES;
+            const uint32_t parity = (it / STAGES) & 1u;
+            mbar_wait(&empty_bar[stage], parity ^ 1u);
+            uint8_t* a_dst = smem + stage * L::STAGE_BYTES;
+            mbar_expect_tx(&full_bar[stage], (uint32_t)L::STAGE_BYTES);
+            tma_load_4d(a_dst, tm, &full_bar[stage], cb * BK, cx, cy, cb_img);
+            tma_load_3d(a_dst + MT * A_BYTES, &tmB, &full_bar[stage], ph.w_k0 + g * BK, c.n0, 0);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------- MMA issuer -----
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BN);
+      uint32_t it = 0, j = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++j) {
+        const int phase_idx = tile / (tiles_m * tiles_n);
+        const int nkb = p.phase[phase_idx].nkb;
+        const uint32_t buf = j & 1u;
+        mbar_wait(&tempty_bar[buf], ((j >> 1) & 1u) ^ 1u);   // epilogue has drained this buffer
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + buf * (MT * BN);
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const uint32_t stage = it % STAGES;
+          const uint32_t parity = (it / STAGES) & 1u;
+          mbar_wait(&full_bar[stage], parity);
+          tcgen05_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * L::STAGE_BYTES);
+          const uint64_t bdesc = make_smem_desc(a_addr + MT * A_BYTES);
+#pragma unroll
+          for (int m = 0; m < MT; ++m) {
+            const uint64_t adesc = make_smem_desc(a_addr + m * A_BYTES);
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k)
+              umma_bf16(d_tmem + m * BN, adesc + 2 * k, bdesc + 2 * k, idesc, (uint32_t)((kb | k) != 0));
+          }
+          umma_commit(&empty_bar[stage]);
+        }
+        umma_commit(&tfull_bar[buf]);
+      }
+    }
+    __syncwarp();
+  } else if (warp < 10) {
+    // --------------------------------------------------- epilogue -----
+    // 8 warps: warp w reads TMEM lane quarter w % 4 (rows 32q..32q+31 of the sub-tile) and
+    // column half (w - 2) / 4 of the current 64-column panel.  Panels are handed to the
+    // store warp through pfull/pempty mbarriers (two staging buffers); the pfull wait doubles
+    // as the barrier after which the staged panel may be read back for the statistics.
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int row = q * 32 + lane;              // accumulator row of this thread, 0..127
+    const int et = (warp - 2) * 32 + lane;      // epilogue thread id 0..255
+    const int rpi = BM / p.bb;                  // rows of one image inside a 128-row sub-tile
+    const int rb = row / rpi;                   // image of this thread's row within the sub-tile
+    const int nsb_img = 8 / p.bb;               // 16-row statistics sub-blocks per image
+    const int tiles_img = p.tiles_x * p.tiles_y;
+    const int cp = et & 31, r8 = et >> 5;       // statistics role: column pair, 16-row sub-block
+    const int st_ch = et & 15, st_ib = et >> 4; // final reduce role: 4-channel chunk, image in sub-tile
+    float2* prev_dst = nullptr;                 // deferred final reduce of the previous panel
+    uint32_t j = 0, pc = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++j) {
+      const TileCoord c = decode_tile(p, tile, tiles_m, tiles_n, BN, MT);
+      const uint32_t buf = j & 1u;
+      int b = c.tb * p.bb + rb;
+      if (b >= p.B) b = p.B - 1;         // rows of a ragged last tile: values are never stored
+      const float* vrow = p.vec ? p.vec + (long long)b * p.vec_stride : nullptr;
+      const float* vrow2 = p.vec2 ? p.vec2 + (long long)b * p.vec2_stride : nullptr;
+      constexpr int NPANEL = BN / PANEL_COLS;
+#pragma unroll 1
+      for (int pi = 0; pi < MT * NPANEL; ++pi, ++pc) {
+        const int m = pi / NPANEL, pn = pi - m * NPANEL;
+        const int n = c.n0 + pn * PANEL_COLS;
+        const int nc = n + half * 32;
+        const int ty = c.ty * MT + m;    // 128-row box index within the image
+        const uint32_t sb = pc & 1u, spar = (pc >> 1) & 1u;
+        uint8_t* sbuf = staging + sb * PANEL_BYTES;
+        // per-column additive terms first: their latency hides behind the waits below
+        float bv[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) bv[i] = 0.f;
+        if (p.bias) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 t4 = __ldg(reinterpret_cast<const float4*>(p.bias + nc) + i);
+            bv[4 * i] = t4.x; bv[4 * i + 1] = t4.y; bv[4 * i + 2] = t4.z; bv[4 * i + 3] = t4.w;
+          }
+        }
+        if (vrow) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 t4 = __ldg(reinterpret_cast<const float4*>(vrow + nc) + i);
+            bv[4 * i] += t4.x; bv[4 * i + 1] += t4.y; bv[4 * i + 2] += t4.z; bv[4 * i + 3] += t4.w;
+          }
+        }
+        if (vrow2) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 t4 = __ldg(reinterpret_cast<const float4*>(vrow2 + nc) + i);
+            bv[4 * i] += t4.x; bv[4 * i + 1] += t4.y; bv[4 * i + 2] += t4.z; bv[4 * i + 3] += t4.w;
+          }
+        }
+        if (pi == 0) {
+          mbar_wait(&tfull_bar[buf], (j >> 1) & 1u);
+          tcgen05_fence_after();
+          if (dbg != nullptr && et == 0 && j < 8) dbg[8 + j] = clock64();
+        }
+        uint32_t v[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * (MT * BN) +
+                               (uint32_t)(m * BN + pn * PANEL_COLS + half * 32);
+        tmem_ld32_nowait(taddr, v);
+        mbar_wait(&pempty_bar[sb], spar ^ 1u);   // the store that last read sbuf has drained it
+        tmem_wait_ld();
+        if (pi == MT * NPANEL - 1) {     // accumulators fully read: hand the buffer back to the MMA warp
+          tcgen05_fence_before();
+          mbar_arrive(&tempty_bar[buf]);
+        }
+        const uint32_t row_addr = smem_u32(sbuf) + (uint32_t)row * 128u;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          float f[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) f[i] = fmaf(__uint_as_float(v[g * 8 + i]), p.alpha, bv[g * 8 + i]);
+          const bf16x8 pk = pack8(f);
+          const uint32_t dst = row_addr + (uint32_t)(((half * 4 + g) ^ (row & 7)) << 4);   // SWIZZLE_128B
+          const uint4 u = *reinterpret_cast<const uint4*>(&pk);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(u.x), "r"(u.y), "r"(u.z),
+                       "r"(u.w)
+                       : "memory");
+        }
+        fence_proxy_async_smem();
+        mbar_arrive(&pfull_bar[sb]);
+        mbar_wait(&pfull_bar[sb], spar);         // every thread's part of the panel is staged
+        if (p.stats != nullptr) {
+          if (prev_dst != nullptr) {             // final reduce of the previous panel's sub-block sums
+            const float2* rd = red + ((pc + 1) & 1u) * 128;
+            float S = 0.f, Q = 0.f;
+            for (int k = 0; k < nsb_img; ++k) {
+              const float2 t2 = rd[(st_ib * nsb_img + k) * 16 + st_ch];
+              S += t2.x;
+              Q += t2.y;
+            }
+            *prev_dst = make_float2(S, Q);
+          }
+          // column sums over the staged bf16 panel: thread = (16-row sub-block, column pair)
+          float s = 0.f, qq = 0.f;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int r = r8 * 16 + i;
+            const uint32_t a = smem_u32(sbuf) + (uint32_t)r * 128u +
+                               (uint32_t)((((cp >> 2) ^ (r & 7)) << 4) | ((cp & 3) << 2));
+            uint32_t wv;
+            asm volatile("ld.shared.b32 %0, [%1];" : "=r"(wv) : "r"(a));
+            const float x0 = __uint_as_float(wv << 16), x1 = __uint_as_float(wv & 0xffff0000u);
+            s += x0 + x1;
+            qq = fmaf(x0, x0, qq);
+            qq = fmaf(x1, x1, qq);
+          }
+          s += __shfl_xor_sync(0xffffffffu, s, 1);
+          qq += __shfl_xor_sync(0xffffffffu, qq, 1);
+          if ((cp & 1) == 0) red[sb * 128 + r8 * 16 + (cp >> 1)] = make_float2(s, qq);
+          prev_dst = nullptr;
+          const int bi = c.tb * p.bb + st_ib;
+          if (et < 16 * p.bb && bi < p.B) {
+            const int part = (p.bb == 1) ? c.phase * tiles_img + ty * p.tiles_x + c.tx : c.phase;
+            prev_dst = reinterpret_cast<float2*>(p.stats) +
+                       ((long long)bi * p.stats_parts + part) * (p.Cout >> 2) + (n >> 2) + st_ch;
+          }
+        }
+      }
+      if (dbg != nullptr && et == 0 && j < 8) dbg[24 + j] = clock64();
+    }
+    if (p.stats != nullptr) {                    // flush the last panel's statistics
+      named_bar_sync(1, P_EPI_THREADS);
+      if (prev_dst != nullptr) {
+        const float2* rd = red + ((pc + 1) & 1u) * 128;
+        float S = 0.f, Q = 0.f;
+        for (int k = 0; k < nsb_img; ++k) {
+          const float2 t2 = rd[(st_ib * nsb_img + k) * 16 + st_ch];
+          S += t2.x;
+          Q += t2.y;
+        }
+        *prev_dst = make_float2(S, Q);
+      }
+    }
+  } else if (warp == 10) {
+    // ------------------------------------------------ output stores ----
+    if (lane == 0) {
+      uint32_t pc = 0;
+      constexpr int NPANEL = BN / PANEL_COLS;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const TileCoord c = decode_tile(p, tile, tiles_m, tiles_n, BN, MT);
+        const DevPhase& ph = p.phase[c.phase];
+        for (int pi = 0; pi < MT * NPANEL; ++pi, ++pc) {
+          const int m = pi / NPANEL, pn = pi - m * NPANEL;
+          const int n = c.n0 + pn * PANEL_COLS;
+          const int ty = c.ty * MT + m;
+          const uint32_t sb = pc & 1u, spar = (pc >> 1) & 1u;
+          const uint8_t* sbuf = staging + sb * PANEL_BYTES;
+          mbar_wait(&pfull_bar[sb], spar);
+          if (p.out_scale == 1)
+            tma_store_3d(&tmOut, sbuf, n, c.tx * p.bw, c.tb * p.bb * p.Hm + ty * p.bh);
+          else
+            tma_store_5d(&tmOut, sbuf, n, ph.px, c.tx * p.bw, ph.py, c.tb * p.bb * p.Hm + ty * p.bh);
+          bulk_commit_group();
+          bulk_wait_group_read<0>();             // shared memory has been read: the buffer is free again
+          mbar_arrive(&pempty_bar[sb]);
+        }
+      }
+      bulk_wait_group<0>();                      // all tensor stores complete before the CTA retires
+    }
+  }
+
+  if (dbg != nullptr && warp == 2 && lane == 0) dbg[3] = clock64();
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"((uint32_t)L::TMEM_COLS)
+                 : "memory");
+  }
+}
+
+// ---------------------------------------------------------------- host ----
+int device_sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
+
+int tapgemm_stats_parts(const TapGemmParams& p) {
+  return p.nphases * (p.bb == 1 ? p.tiles_x * p.tiles_y : 1);
+}
+
+static int persist_bn(const its_conv_desc* d, const TapGemmParams& p) {
+  if (d->bn != 0) return d->bn;
+  return (p.Cout % 256 == 0) ? 256 : (p.Cout % 192 == 0) ? 192 : (p.Cout % 128 == 0) ? 128 : 64;
+}
+
+bool tapgemm_persist_eligible(const its_conv_desc* d, const TapGemmParams& p) {
+  if (p.out_fp32 || p.out_nchw || p.splits > 1 || p.w_batch_stride != 0 || p.res != nullptr) return false;
+  if (p.Cout % 64 != 0 || p.out_c_pitch % 8 != 0) return false;
+  const int bn = persist_bn(d, p);
+  if (!(bn == 64 || bn == 128 || bn == 192 || bn == 256) || p.Cout % bn != 0) return false;
+  if (p.bw * p.bh * p.bb != BM || p.Wm % p.bw != 0 || p.Hm % p.bh != 0) return false;
+  if (p.bb > 1 && p.bh != p.Hm) return false;
+  for (int s = 0; s < p.nsrc; ++s)
+    if (p.src[s].bcast) return false;
+  return true;
+}
+
+template <int BN, int STAGES, int MT>
+static int launch_persist(const TapGemmParams& p, const CUtensorMap* tmA, const CUtensorMap& tmB,
+                          const CUtensorMap& tmOut, cudaStream_t stream) {
+  using L = PersistSmem<BN, STAGES, MT>;
+  static_assert(L::TOTAL <= 227 * 1024, "shared memory budget");
+  auto kern = tapgemm_persist_kernel<BN, STAGES, MT>;
+  static bool configured = false;
+  if (!configured) {
+    ITS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    configured = true;
+  }
+  const int tiles = p.tiles_x * (p.tiles_y / MT) * p.tiles_b * (p.Cout / BN) * p.nphases;
+  const int sms = device_sm_count();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(tiles < sms ? tiles : sms, 1, 1);
+  cfg.blockDim = dim3(P_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = L::TOTAL;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  ITS_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, p, tmA[0], tmA[1], tmA[2], tmB, tmOut));
+  return ITS_OK;
+}
+
+int tapgemm_launch_persist(const its_conv_desc* d, const TapGemmParams& p, cudaStream_t stream) {
+  const int bn = persist_bn(d, p);
+  ITS_REQUIRE(tapgemm_persist_eligible(d, p), "its_conv_igemm: layer not eligible for the persistent kernel");
+  ITS_REQUIRE(p.w_pitch % 8 == 0 && (reinterpret_cast<uintptr_t>(p.w) & 15) == 0, "its_conv_igemm: weight alignment");
+  ITS_REQUIRE((reinterpret_cast<uintptr_t>(p.out) & 15) == 0, "its_conv_igemm: output pointer alignment");
+  if (p.stats != nullptr)
+    ITS_REQUIRE(p.stats_parts == tapgemm_stats_parts(p), "its_conv_igemm: stats_parts=%d, the tiling writes %d",
+                p.stats_parts, tapgemm_stats_parts(p));
+  // two row boxes per tile (shared weight tiles) when the N tile leaves TMEM room for two
+  // double-buffered accumulators and a tile of 2 x bh rows still tiles the image
+  const int mt = (bn <= 128 && p.bb == 1 && p.tiles_y % 2 == 0 && d->cluster != 1) ? 2 : 1;
+  CUtensorMap tmA[ITS_MAX_SRC], tmB, tmOut;
+  int rc = tapgemm_encode_operand_maps(p, bn, tmA, &tmB, mt);
+  if (rc != ITS_OK) return rc;
+  const cuuint64_t pitch_b = (cuuint64_t)p.out_c_pitch * 2;
+  if (p.out_scale == 1) {
+    // [B*Hm][Wm][C]: image and row merge into one dimension (a tile spanning images covers whole images)
+    const cuuint64_t dims[3] = {(cuuint64_t)p.Cout, (cuuint64_t)p.Wm, (cuuint64_t)p.B * p.Hm};
+    const cuuint64_t strides[2] = {pitch_b, pitch_b * p.Wout};
+    const cuuint32_t box[3] = {(cuuint32_t)PANEL_COLS, (cuuint32_t)p.bw, (cuuint32_t)(p.bh * p.bb)};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    rc = encode_bf16_map(&tmOut, 3, p.out, dims, strides, box, estr, "output");
+  } else {
+    // sub-pixel phases: [B*Hm][py][Wm][px][C] view of the [B][2Hm][2Wm][C] tensor
+    const cuuint64_t dims[5] = {(cuuint64_t)p.Cout, (cuuint64_t)p.out_scale, (cuuint64_t)p.Wm,
+                                (cuuint64_t)p.out_scale, (cuuint64_t)p.B * p.Hm};
+    const cuuint64_t strides[4] = {pitch_b, pitch_b * p.out_scale, pitch_b * p.Wout,
+                                   pitch_b * p.Wout * p.out_scale};
+    const cuuint32_t box[5] = {(cuuint32_t)PANEL_COLS, 1, (cuuint32_t)p.bw, 1, (cuuint32_t)(p.bh * p.bb)};
+    const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    rc = encode_bf16_map(&tmOut, 5, p.out, dims, strides, box, estr, "output");
+  }
+  if (rc != ITS_OK) return rc;
+  if (mt == 2) {
+    if (bn == 64) return launch_persist<64, 4, 2>(p, tmA, tmB, tmOut, stream);
+    return launch_persist<128, 4, 2>(p, tmA, tmB, tmOut, stream);
+  }
+  switch (bn) {
+    case 64:  return launch_persist<64, 6, 1>(p, tmA, tmB, tmOut, stream);
+    case 128: return launch_persist<128, 5, 1>(p, tmA, tmB, tmOut, stream);
+    case 192: return launch_persist<192, 4, 1>(p, tmA, tmB, tmOut, stream);
+    default:  return launch_persist<256, 4, 1>(p, tmA, tmB, tmOut, stream);
+  }
+}
+
+}  // namespace its

@@ -1,9 +1,19 @@
 // Fused DDPM ancestral update: guidance mix + posterior mean + noise + NaN flag
 // + final clip, one coalesced float4 pass (HBM-bound).  See include/its_b200.h.
 #include "its_common.cuh"
+#include <stdlib.h>
 #include <stdarg.h>
 
 namespace its {
+
+static int g_pdl = -1;   // -1: read ITS_PDL from the environment on first use (default on)
+bool pdl_enabled() {
+  if (g_pdl < 0) {
+    const char* e = getenv("ITS_PDL");
+    g_pdl = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return g_pdl != 0;
+}
 
 char* err_buf() {
   static thread_local char buf[512] = "";
@@ -24,6 +34,7 @@ __global__ void __launch_bounds__(256) ddpm_step_kernel(
     const float* __restrict__ noise, long long noise_t_stride, long long n_img, long long quads_per_img,
     const float* __restrict__ coef, const int* __restrict__ t_dev, float w, float opw, uint64_t seed,
     long long cand_id0, int* __restrict__ nan_flag, int clip_last) {
+  pdl_prologue();
   const int t = *t_dev;
   const float4 cf = *reinterpret_cast<const float4*>(coef + 4 * (long long)t);
   const float c1 = cf.x, c2 = cf.y, sigma = (t > 0) ? cf.z : 0.0f;
@@ -76,6 +87,7 @@ __global__ void __launch_bounds__(256) ddpm_step_kernel(
 __global__ void __launch_bounds__(256) philox_normal_kernel(
     float* __restrict__ out, const float* __restrict__ base, int base_bcast, float scale,
     long long n_img, long long quads_per_img, uint64_t seed, long long cand_id0, uint32_t tag) {
+  pdl_prologue();
   const long long total = n_img * quads_per_img;
   for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < total;
        q += (long long)gridDim.x * blockDim.x) {
@@ -92,7 +104,10 @@ __global__ void __launch_bounds__(256) philox_normal_kernel(
   }
 }
 
-__global__ void step_advance_kernel(int* t_dev, int delta) { *t_dev += delta; }
+__global__ void step_advance_kernel(int* t_dev, int delta) {
+  pdl_prologue();
+  *t_dev += delta;
+}
 
 static int grid_for(long long work_items, int block) {
   long long g = (work_items + block - 1) / block;
@@ -110,6 +125,11 @@ extern "C" int its_abi_sizeof(int which) {
   return which == 0 ? (int)sizeof(its_conv_desc) : which == 1 ? (int)sizeof(its_src_t)
                                                               : (int)sizeof(its_phase_t);
 }
+extern "C" int its_set_pdl(int32_t enabled) {
+  its::g_pdl = enabled ? 1 : 0;
+  return ITS_OK;
+}
+
 extern "C" int its_device_sm_count(int* out_host) {
   int dev = 0;
   ITS_CHECK_CUDA(cudaGetDevice(&dev));
@@ -126,7 +146,7 @@ extern "C" int its_ddpm_step(float* x, const float* eps_c, const float* eps_u, c
               "its_ddpm_step: n_per_img=%lld must be a positive multiple of 4", (long long)n_per_img);
   ITS_REQUIRE(noise_t_stride % 4 == 0, "its_ddpm_step: noise_t_stride must be a multiple of 4");
   const long long quads = n_per_img / 4;
-  its::ddpm_step_kernel<<<its::grid_for(n_img * quads, 256), 256, 0, its::as_stream(stream)>>>(
+  ITS_LAUNCH(its::ddpm_step_kernel, dim3(its::grid_for(n_img * quads, 256)), dim3(256), 0, its::as_stream(stream), 
       x, eps_c, eps_u, noise, noise_t_stride, n_img, quads, coef, t_dev, (float)w, (float)(1.0 + w), seed,
       cand_id0,
       nan_flag, clip_last);
@@ -141,7 +161,7 @@ extern "C" int its_philox_normal(float* out, const float* base, int32_t base_bca
   ITS_REQUIRE(n_img > 0 && n_per_img > 0 && n_per_img % 4 == 0,
               "its_philox_normal: n_per_img=%lld must be a positive multiple of 4", (long long)n_per_img);
   const long long quads = n_per_img / 4;
-  its::philox_normal_kernel<<<its::grid_for(n_img * quads, 256), 256, 0, its::as_stream(stream)>>>(
+  ITS_LAUNCH(its::philox_normal_kernel, dim3(its::grid_for(n_img * quads, 256)), dim3(256), 0, its::as_stream(stream), 
       out, base, base_bcast, scale, n_img, quads, seed, cand_id0, (uint32_t)tag);
   ITS_CHECK_LAUNCH();
   return ITS_OK;
@@ -149,7 +169,7 @@ extern "C" int its_philox_normal(float* out, const float* base, int32_t base_bca
 
 extern "C" int its_step_advance(int32_t* t_dev, int32_t delta, void* stream) {
   ITS_REQUIRE(t_dev, "its_step_advance: null pointer");
-  its::step_advance_kernel<<<1, 1, 0, its::as_stream(stream)>>>(t_dev, delta);
+  ITS_LAUNCH(its::step_advance_kernel, dim3(1), dim3(1), 0, its::as_stream(stream), t_dev, delta);
   ITS_CHECK_LAUNCH();
   return ITS_OK;
 }

@@ -7,6 +7,7 @@ namespace its {
 __global__ void time_embed_kernel(float* __restrict__ out, const long long* __restrict__ t_idx,
                                   const int* __restrict__ t_dev, const float* __restrict__ freq,
                                   int n_rows, int half) {
+  pdl_prologue();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_rows * half) return;
   const int b = i / half, j = i - b * half;
@@ -20,6 +21,7 @@ __global__ void time_embed_kernel(float* __restrict__ out, const long long* __re
 __global__ void embed_rows_kernel(float* __restrict__ out, const float* __restrict__ table,
                                   const long long* __restrict__ idx, const int* __restrict__ t_dev,
                                   int n_rows, int dim, int n_table_rows) {
+  pdl_prologue();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_rows * dim) return;
   const int b = i / dim, j = i - b * dim;
@@ -35,6 +37,7 @@ __global__ void __launch_bounds__(256) linear_kernel(float* __restrict__ y, cons
                                                      const float* __restrict__ bias, int n_rows,
                                                      int K, int N, int silu_in, int silu_out,
                                                      int accumulate) {
+  pdl_prologue();
   const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= (long long)n_rows * N) return;
@@ -63,7 +66,7 @@ extern "C" int its_time_embed(float* out, const int64_t* t_idx, const int32_t* t
   ITS_REQUIRE(out && freq && (t_idx || t_dev), "its_time_embed: null pointer");
   ITS_REQUIRE(n_rows > 0 && d_model > 0 && d_model % 2 == 0, "its_time_embed: bad d_model=%d", d_model);
   const int half = d_model / 2, total = n_rows * half;
-  its::time_embed_kernel<<<(total + 127) / 128, 128, 0, its::as_stream(stream)>>>(
+  ITS_LAUNCH(its::time_embed_kernel, dim3((total + 127) / 128), dim3(128), 0, its::as_stream(stream), 
       out, reinterpret_cast<const long long*>(t_idx), t_dev, freq, n_rows, half);
   ITS_CHECK_LAUNCH();
   return ITS_OK;
@@ -74,7 +77,7 @@ extern "C" int its_embed_rows(float* out, const float* table, const int64_t* idx
   ITS_REQUIRE(out && table && (idx || t_dev), "its_embed_rows: null pointer");
   ITS_REQUIRE(n_rows > 0 && dim > 0 && n_table_rows > 0, "its_embed_rows: bad sizes");
   const int total = n_rows * dim;
-  its::embed_rows_kernel<<<(total + 127) / 128, 128, 0, its::as_stream(stream)>>>(
+  ITS_LAUNCH(its::embed_rows_kernel, dim3((total + 127) / 128), dim3(128), 0, its::as_stream(stream), 
       out, table, reinterpret_cast<const long long*>(idx), t_dev, n_rows, dim, n_table_rows);
   ITS_CHECK_LAUNCH();
   return ITS_OK;
@@ -88,7 +91,7 @@ extern "C" int its_linear(float* y, const float* x, const float* W, const float*
   const long long warps = (long long)n_rows * N;
   const long long blocks = (warps * 32 + 255) / 256;
   ITS_REQUIRE(blocks < (1LL << 31), "its_linear: too large");
-  its::linear_kernel<<<(unsigned)blocks, 256, 0, its::as_stream(stream)>>>(
+  ITS_LAUNCH(its::linear_kernel, dim3((unsigned)blocks), dim3(256), 0, its::as_stream(stream), 
       y, x, W, bias, n_rows, K, N, silu_in, silu_out, accumulate);
   ITS_CHECK_LAUNCH();
   return ITS_OK;

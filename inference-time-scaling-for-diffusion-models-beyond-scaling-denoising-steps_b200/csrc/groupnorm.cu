@@ -13,6 +13,7 @@ namespace its {
 constexpr int GN_THREADS = 256;
 constexpr int GN_MAX_VEC = 128;  // C <= 1024
 
+
 struct GnArgs {
   const __nv_bfloat16* src0;
   const __nv_bfloat16* src1;
@@ -32,6 +33,7 @@ __device__ __forceinline__ bf16x8 gn_load(const GnArgs& a, long long pix, int c0
 }
 
 __global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(const GnArgs a) {
+  pdl_prologue();
   __shared__ float s_sum[GN_THREADS * 8];
   __shared__ float s_sq[GN_THREADS * 8];
   const int nvec = a.C / 8;
@@ -81,6 +83,7 @@ __global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(const GnArgs a) {
 }
 
 __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const GnArgs a) {
+  pdl_prologue();
   __shared__ float s_mean[64], s_rstd[64];
   const int tid = threadIdx.x;
   const int chunk = blockIdx.x, img = blockIdx.y;
@@ -134,6 +137,7 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const GnArgs a) {
 // which they kept in shared memory (CACHE) — one global read + one write per element.
 template <bool CACHE>
 __global__ void __launch_bounds__(GN_THREADS) gn_cluster_kernel(const GnArgs a) {
+  pdl_prologue();
   namespace cg = cooperative_groups;
   cg::cluster_group cluster = cg::this_cluster();
   extern __shared__ __align__(16) unsigned char gn_dyn[];
@@ -236,6 +240,112 @@ __global__ void __launch_bounds__(GN_THREADS) gn_cluster_kernel(const GnArgs a) 
   }
 }
 
+
+// ---- apply-only variant: statistics come from the producing tap-GEMM ----------------
+// The persistent tap-GEMM (conv_persist_sm100.cu) leaves, for the tensor it stores, the sum
+// and the sum of squares of every (image, 4-channel chunk, tile) in a partial-sum array
+// [n_img][parts][C/4] of float2.  This kernel reduces them per group in a fixed order in
+// double (tpg lanes per group, xor-shuffle tree), then streams the tensor once:
+// 16-byte load -> scale/shift(+Swish) -> 16-byte store.
+struct GnStatArgs {
+  const __nv_bfloat16* src0;
+  const __nv_bfloat16* src1;
+  __nv_bfloat16* out;
+  const float* gamma;
+  const float* beta;
+  const float2* st0;
+  const float2* st1;
+  int C0, C1, C, HW, groups, parts0, parts1, silu, chunks;
+  float eps;
+};
+
+__global__ void __launch_bounds__(GN_THREADS) gn_apply_stats_kernel(const GnStatArgs a) {
+  pdl_prologue();
+  __shared__ float s_mean[64], s_rstd[64];
+  __shared__ float2 s_ab[8 * GN_MAX_VEC];
+  const int tid = threadIdx.x;
+  const int chunk = blockIdx.x, img = blockIdx.y;
+  const int cg = a.C / a.groups;         // channels per group (multiple of 4)
+  const int cg4 = cg >> 2;
+  const int tpg = GN_THREADS / a.groups; // lanes per group: power of two, <= 32
+  {
+    const int g = tid / tpg, l = tid - g * tpg;
+    double s = 0.0, q = 0.0;
+    if (g < a.groups) {
+      for (int kk = 0; kk < cg4; ++kk) {
+        int k = g * cg4 + kk;            // 4-channel chunk in the concatenated channel space
+        const float2* st;
+        int parts, nchunk;
+        if (k < (a.C0 >> 2)) { st = a.st0; parts = a.parts0; nchunk = a.C0 >> 2; }
+        else { st = a.st1; parts = a.parts1; nchunk = a.C1 >> 2; k -= (a.C0 >> 2); }
+        for (int part = l; part < parts; part += tpg) {
+          const float2 v = __ldg(st + ((long long)img * parts + part) * nchunk + k);
+          s += (double)v.x;
+          q += (double)v.y;
+        }
+      }
+    }
+    for (int o = tpg >> 1; o > 0; o >>= 1) {
+      s += __shfl_xor_sync(0xffffffffu, s, o);
+      q += __shfl_xor_sync(0xffffffffu, q, o);
+    }
+    if (g < a.groups && l == 0) {
+      const double n = (double)cg * (double)a.HW;
+      const double mean = s / n;
+      double var = q / n - mean * mean;  // biased, like nn.GroupNorm
+      if (var < 0.0) var = 0.0;
+      s_mean[g] = (float)mean;
+      s_rstd[g] = (float)(1.0 / sqrt(var + (double)a.eps));
+    }
+  }
+  __syncthreads();
+  for (int c = tid; c < a.C; c += GN_THREADS) {
+    const int g = c / cg;
+    const float sc = s_rstd[g] * __ldg(a.gamma + c);
+    s_ab[c] = make_float2(sc, __ldg(a.beta + c) - s_mean[g] * sc);
+  }
+  __syncthreads();
+  const int nvec = a.C / 8;
+  const int prow = GN_THREADS / nvec;
+  const int cv = tid % nvec, pl = tid / nvec;
+  if (pl >= prow) return;
+  float scale[8], shift[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float2 ab = s_ab[cv * 8 + i];
+    scale[i] = ab.x;
+    shift[i] = ab.y;
+  }
+  const int per = (a.HW + a.chunks - 1) / a.chunks;
+  const int p0 = chunk * per, p1 = min(a.HW, p0 + per);
+  const bool from0 = cv * 8 < a.C0;
+  const __nv_bfloat16* sp = from0 ? a.src0 + cv * 8 : a.src1 + (cv * 8 - a.C0);
+  const int spitch = from0 ? a.C0 : a.C1;
+  constexpr int U = 4;                   // independent 16-byte loads in flight per thread
+  for (int pb = p0 + pl; pb < p1; pb += prow * U) {
+    bf16x8 raw[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int p = pb + u * prow;
+      if (p < p1) raw[u] = *reinterpret_cast<const bf16x8*>(sp + ((long long)img * a.HW + p) * spitch);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int p = pb + u * prow;
+      if (p < p1) {
+        float f[8];
+        unpack8(raw[u], f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float v = fmaf(f[i], scale[i], shift[i]);
+          f[i] = a.silu ? silu_f(v) : v;
+        }
+        *reinterpret_cast<bf16x8*>(a.out + ((long long)img * a.HW + p) * a.C + cv * 8) = pack8(f);
+      }
+    }
+  }
+}
+
 template <bool CACHE>
 static int launch_gn_cluster(const GnArgs& a, int n_img, size_t dyn_bytes, cudaStream_t stream) {
   auto kern = gn_cluster_kernel<CACHE>;
@@ -249,13 +359,15 @@ static int launch_gn_cluster(const GnArgs& a, int n_img, size_t dyn_bytes, cudaS
   cfg.blockDim = dim3(GN_THREADS, 1, 1);
   cfg.dynamicSmemBytes = dyn_bytes;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = a.chunks;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   ITS_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, a));
   return ITS_OK;
 }
@@ -289,9 +401,42 @@ extern "C" int its_group_norm(void* out, const void* src0, int32_t C0, const voi
     return launch_gn_cluster<false>(a, n_img, 0, as_stream(stream));
   }
   dim3 grid(chunks, n_img);
-  gn_stats_kernel<<<grid, GN_THREADS, 0, as_stream(stream)>>>(a);
+  ITS_LAUNCH(gn_stats_kernel, dim3(grid), dim3(GN_THREADS), 0, as_stream(stream), a);
   ITS_CHECK_LAUNCH();
-  gn_apply_kernel<<<grid, GN_THREADS, 0, as_stream(stream)>>>(a);
+  ITS_LAUNCH(gn_apply_kernel, dim3(grid), dim3(GN_THREADS), 0, as_stream(stream), a);
+  ITS_CHECK_LAUNCH();
+  return ITS_OK;
+}
+
+extern "C" int its_group_norm_apply(void* out, const void* src0, int32_t C0, const float* stats0,
+                                    int32_t parts0, const void* src1, int32_t C1, const float* stats1,
+                                    int32_t parts1, const float* gamma, const float* beta, int32_t n_img,
+                                    int32_t HW, int32_t groups, float eps, int32_t silu, void* stream) {
+  using namespace its;
+  ITS_REQUIRE(out && src0 && stats0 && gamma && beta, "its_group_norm_apply: null pointer");
+  ITS_REQUIRE(C1 == 0 || (src1 != nullptr && stats1 != nullptr), "its_group_norm_apply: C1 > 0 needs src1 and stats1");
+  const int C = C0 + C1;
+  ITS_REQUIRE(C0 > 0 && C0 % 8 == 0 && C1 % 8 == 0 && C <= 8 * GN_MAX_VEC,
+              "its_group_norm_apply: channels (%d+%d) must be multiples of 8 and <= %d", C0, C1, 8 * GN_MAX_VEC);
+  ITS_REQUIRE(groups > 0 && groups <= 64 && (groups & (groups - 1)) == 0 && C % groups == 0 && (C / groups) % 4 == 0,
+              "its_group_norm_apply: groups=%d must be a power of two dividing C=%d into multiples of 4 channels", groups, C);
+  ITS_REQUIRE(n_img > 0 && HW > 0 && parts0 > 0 && (C1 == 0 || parts1 > 0), "its_group_norm_apply: bad n_img/HW/parts");
+  GnStatArgs a;
+  a.src0 = static_cast<const __nv_bfloat16*>(src0);
+  a.src1 = static_cast<const __nv_bfloat16*>(src1);
+  a.out = static_cast<__nv_bfloat16*>(out);
+  a.gamma = gamma; a.beta = beta;
+  a.st0 = reinterpret_cast<const float2*>(stats0);
+  a.st1 = reinterpret_cast<const float2*>(stats1);
+  a.C0 = C0; a.C1 = C1; a.C = C; a.HW = HW; a.groups = groups; a.parts0 = parts0; a.parts1 = parts1;
+  a.silu = silu; a.eps = eps;
+  // ~32 KB of activations per CTA keeps >= 2 waves on 148 SMs for the large maps
+  long long chunks = ((long long)HW * C * 2 + 32767) / 32768;
+  if (chunks < 1) chunks = 1;
+  if (chunks > HW) chunks = HW;
+  a.chunks = (int)chunks;
+  dim3 grid((unsigned)chunks, (unsigned)n_img);
+  ITS_LAUNCH(gn_apply_stats_kernel, dim3(grid), dim3(GN_THREADS), 0, as_stream(stream), a);
   ITS_CHECK_LAUNCH();
   return ITS_OK;
 }

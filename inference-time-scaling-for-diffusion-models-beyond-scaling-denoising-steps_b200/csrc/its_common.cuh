@@ -31,6 +31,31 @@ int set_error(int code, const char* fmt, ...);
 
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
+// Programmatic dependent launch: every kernel of the library starts with pdl_prologue()
+// (release the next launch, then wait for the previous grid's memory to be visible), so
+// consecutive launches on a stream overlap their launch latency / set-up with the tail of
+// the predecessor.  its_set_pdl(0) turns the launch attribute off (plain stream order).
+bool pdl_enabled();
+__device__ __forceinline__ void pdl_prologue() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+#define ITS_LAUNCH(kernel_, grid_, block_, smem_, stream_, ...)                                   \
+  do {                                                                                         \
+    cudaLaunchConfig_t _cfg = {};                                                              \
+    _cfg.gridDim = (grid_);                                                                    \
+    _cfg.blockDim = (block_);                                                                  \
+    _cfg.dynamicSmemBytes = (smem_);                                                           \
+    _cfg.stream = (stream_);                                                                   \
+    cudaLaunchAttribute _at[1];                                                                \
+    _at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                            \
+    _at[0].val.programmaticStreamSerializationAllowed = 1;                                     \
+    _cfg.attrs = _at;                                                                          \
+    _cfg.numAttrs = ::its::pdl_enabled() ? 1 : 0;                                              \
+    ITS_CHECK_CUDA(cudaLaunchKernelEx(&_cfg, kernel_, __VA_ARGS__));                           \
+  } while (0)
+
 __device__ __forceinline__ float silu_f(float v) { return v / (1.0f + __expf(-v)); }
 
 __device__ __forceinline__ float warp_sum(float v) {

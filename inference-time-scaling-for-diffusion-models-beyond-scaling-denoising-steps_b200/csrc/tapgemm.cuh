@@ -2,6 +2,7 @@
 // (conv_igemm_sm100.cu) and its CUDA-core reference twin (conv_direct.cu).
 #pragma once
 #include "its_common.cuh"
+#include <cuda.h>  // CUtensorMap (types only; the encoder is fetched at run time)
 
 namespace its {
 
@@ -39,6 +40,8 @@ struct TapGemmParams {
   int splits;                // split-K factor (>= 1)
   float* ws;                 // [nphases][splits][B*Hm*Wm][Cout] fp32 partial sums
   long long* dbg;            // optional per-CTA clock stamps (diagnostics)
+  float* stats;              // GroupNorm partial sums [B][stats_parts][Cout/4][2] or null (persistent kernel)
+  int stats_parts;
   // M tiling: a 128-row tile is a (bb images) x (bh rows) x (bw cols) box
   int bw, bh, bb, tiles_x, tiles_y, tiles_b;
 };
@@ -47,5 +50,16 @@ struct TapGemmParams {
 int tapgemm_build_params(const its_conv_desc* d, TapGemmParams* p, bool need_k64);
 int tapgemm_launch_ref(const TapGemmParams& p, cudaStream_t stream);
 int tapgemm_launch_sm100(const its_conv_desc* d, const TapGemmParams& p, cudaStream_t stream);
+// persistent variant (conv_persist_sm100.cu): bf16 NHWC output by TMA store, shared weights, no split-K
+bool tapgemm_persist_eligible(const its_conv_desc* d, const TapGemmParams& p);
+int tapgemm_launch_persist(const its_conv_desc* d, const TapGemmParams& p, cudaStream_t stream);
+// number of GroupNorm partial-sum slots per image the persistent kernel writes for this tiling
+int tapgemm_stats_parts(const TapGemmParams& p);
+int encode_bf16_map(CUtensorMap* tm, int rank, const void* base, const cuuint64_t* dims,
+                    const cuuint64_t* strides_bytes, const cuuint32_t* box, const cuuint32_t* estr,
+                    const char* what);
+int tapgemm_encode_operand_maps(const TapGemmParams& p, int b_box_rows, CUtensorMap* tmA, CUtensorMap* tmB_out,
+                                int row_boxes);
+int device_sm_count();
 
 }  // namespace its

@@ -32,6 +32,7 @@ __global__ void __launch_bounds__(256) image_stats_kernel(float* __restrict__ st
                                                           float* __restrict__ feats,
                                                           const float* __restrict__ images, int C,
                                                           int H, int W) {
+  pdl_prologue();
   __shared__ float s_red[32];
   __shared__ float s_feat[4 * 64];
   const int img = blockIdx.x, tid = threadIdx.x;
@@ -82,6 +83,7 @@ __global__ void __launch_bounds__(128) candidate_scores_kernel(float* __restrict
                                                                const float* __restrict__ feats,
                                                                int n_cand, int per_cand,
                                                                int feat_dim, int kind) {
+  pdl_prologue();
   const int cand = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (cand >= n_cand) return;
@@ -131,6 +133,7 @@ __device__ __forceinline__ Best better(Best a, Best b) {
 __global__ void __launch_bounds__(1024) argmax_first_kernel(int* __restrict__ idx_out,
                                                             float* __restrict__ val_out,
                                                             const float* __restrict__ scores, int n) {
+  pdl_prologue();
   __shared__ float s_v[32];
   __shared__ int s_i[32];
   Best b = {-INFINITY, -1};
@@ -165,7 +168,7 @@ extern "C" int its_image_stats(float* stats, float* feats, const float* images, 
   ITS_REQUIRE(stats && images, "its_image_stats: null pointer");
   ITS_REQUIRE(n_img > 0 && C > 0 && C <= 4 && H > 0 && W > 0 && (long long)C * H * W > 1,
               "its_image_stats: unsupported shape C=%d H=%d W=%d", C, H, W);
-  its::image_stats_kernel<<<n_img, 256, 0, its::as_stream(stream)>>>(stats, feats, images, C, H, W);
+  ITS_LAUNCH(its::image_stats_kernel, dim3(n_img), dim3(256), 0, its::as_stream(stream), stats, feats, images, C, H, W);
   ITS_CHECK_LAUNCH();
   return ITS_OK;
 }
@@ -177,7 +180,7 @@ extern "C" int its_candidate_scores(float* scores, const float* stats, const flo
   ITS_REQUIRE(n_cand > 0 && per_cand > 0 && kind >= 0 && kind <= 2, "its_candidate_scores: bad arguments");
   ITS_REQUIRE(kind != 2 || (feats != nullptr && feat_dim > 0), "its_candidate_scores: kind 2 needs feats");
   const int blocks = (n_cand * 32 + 127) / 128;
-  its::candidate_scores_kernel<<<blocks, 128, 0, its::as_stream(stream)>>>(scores, stats, feats, n_cand,
+  ITS_LAUNCH(its::candidate_scores_kernel, dim3(blocks), dim3(128), 0, its::as_stream(stream), scores, stats, feats, n_cand,
                                                                           per_cand, feat_dim, kind);
   ITS_CHECK_LAUNCH();
   return ITS_OK;
@@ -186,7 +189,7 @@ extern "C" int its_candidate_scores(float* scores, const float* stats, const flo
 extern "C" int its_argmax_first(int32_t* idx_out, float* val_out, const float* scores, int32_t n,
                                 void* stream) {
   ITS_REQUIRE(idx_out && val_out && scores && n > 0, "its_argmax_first: bad arguments");
-  its::argmax_first_kernel<<<1, 1024, 0, its::as_stream(stream)>>>(idx_out, val_out, scores, n);
+  ITS_LAUNCH(its::argmax_first_kernel, dim3(1), dim3(1024), 0, its::as_stream(stream), idx_out, val_out, scores, n);
   ITS_CHECK_LAUNCH();
   return ITS_OK;
 }

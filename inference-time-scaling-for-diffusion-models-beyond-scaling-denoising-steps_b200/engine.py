@@ -80,6 +80,7 @@ class UNetPlan:
         self.n_launches, self.flops = 0, 0
         self.gn_partials, self.tproj, self.cproj = None, None, None
         self.ws, self.split_k = None, True
+        self.stats_of, self.schedule, self.fold_residual = {}, 0, True
         return self
 
     # ------------------------------------------------------------ buffers --
@@ -134,7 +135,7 @@ class UNetPlan:
 
     def conv(self, srcs, phases, Hm, Wm, w, cout, *, out=None, out_scale=1, bias=None, vec=None,
              vec_off=0, vec2=None, vec2_off=0, res=None, alpha=1.0, out_fp32=False, w_batch_stride=0,
-             w_pitch=None, B=None, out_shape=None, out_nchw=False) -> torch.Tensor:
+             w_pitch=None, B=None, out_shape=None, out_nchw=False, want_stats=True) -> torch.Tensor:
         """Append one tap-GEMM launch.  srcs: list of (tensor NHWC, C_used, c_off, stride, bcast);
         phases: list of (taps[(src,dy,dx)], w_k0, py, px)."""
         B = self.n_img if B is None else B
@@ -167,6 +168,7 @@ class UNetPlan:
         if res is not None:
             d.res, d.res_c_pitch, d.res_c_off = res.data_ptr(), res.shape[-1], 0
         d.alpha, d.bn, d.out_nchw = alpha, 0, int(out_nchw)
+        d.schedule = self.schedule
         impl = self._impl_for([s[1] for s in srcs], cout, out_nchw)
         launches = 1
         if impl == 0 and not out_nchw and self.split_k:
@@ -178,6 +180,31 @@ class UNetPlan:
                     self.ws = self._new((need,), torch.float32)
                 d.splits, d.ws, d.ws_elems = splits, self.ws.data_ptr(), self.ws.numel()
                 launches = 2
+        if (res is not None and impl == 0 and d.splits <= 1 and self.fold_residual and self.schedule != 1
+                and len(phases) == 1 and alpha == 1.0 and not out_fp32 and not out_nchw and not w_batch_stride
+                and len(srcs) < _lib.MAX_SRC and cout % 64 == 0 and res.shape[-1] == cout
+                and (w_pitch or w.shape[-1]) == w.shape[-1] and w.dim() == 2):
+            # identity shortcut as one more K block with identity weights (exact: 1.0 * bf16 value in
+            # the fp32 accumulator), so the layer runs on the persistent schedule, which has no
+            # residual read in its epilogue
+            k_used = sum(srcs[si][1] for si, _, _ in phases[0][0])
+            w = self._hold(torch.cat([w[:, :k_used].float(), torch.eye(cout, device=w.device)], 1), BF16)
+            i = d.nsrc
+            sN = d.src[i]
+            sN.ptr, sN.c_pitch, sN.c_off, sN.C = res.data_ptr(), res.shape[-1], 0, cout
+            sN.H, sN.W, sN.stride, sN.bcast = res.shape[1], res.shape[2], 1, 0
+            d.nsrc = i + 1
+            ph = d.phase[0]
+            ph.src[ph.ntaps], ph.dy[ph.ntaps], ph.dx[ph.ntaps] = i, 0, 0
+            ph.ntaps += 1
+            d.w, d.w_pitch = w.data_ptr(), w.shape[-1]
+            d.res = None
+        if impl == 0 and want_stats:
+            parts = self.L.its_conv_stats_parts(C.byref(d))
+            if parts > 0:
+                st = self._new((B, parts, cout // 4, 2), torch.float32)
+                d.stats, d.stats_parts = st.data_ptr(), parts
+                self.stats_of[out.data_ptr()] = (st, parts)
         self.descs.append(d)
         self._op(self.L.its_conv_igemm, C.byref(d), impl, flops=flops, launches=launches,
                  kind="tapgemm_sm100" if impl == 0 else "tapgemm_cudacore")
@@ -191,6 +218,17 @@ class UNetPlan:
         Ct = C0 + C1
         out = self._new((B, H, W, Ct))
         HW = H * W
+        st = [self.stats_of.get(t.data_ptr()) for t in srcs]
+        if all(x is not None for x in st) and (Ct // gn.num_groups) % 4 == 0:
+            # statistics were left behind by the producing tap-GEMMs: one streaming apply pass
+            gamma, beta = self._hold(gn.weight, torch.float32), self._hold(gn.bias, torch.float32)
+            s0, p0 = st[0]
+            s1, p1 = st[1] if x1 is not None else (None, 0)
+            self._op(self.L.its_group_norm_apply, out.data_ptr(), x0.data_ptr(), C0, s0.data_ptr(), p0, _ptr(x1), C1,
+                     _ptr(s1), p1, gamma.data_ptr(), beta.data_ptr(), B, HW, gn.num_groups, float(gn.eps),
+                     int(silu), launches=1, kind="group_norm_apply")
+            self.gn_bytes = getattr(self, "gn_bytes", 0) + B * HW * Ct * 2 * 2
+            return out
         prow = max(1, 256 // (Ct // 8))
         # the split depends on (HW, C) only, never on the batch: a candidate's numbers are then
         # bit-identical whatever batch / rank it is evaluated in (fixed summation order)
@@ -260,7 +298,7 @@ class UNetPlan:
         if tensor_path:
             wqk = self._hold(torch.cat([wq, wk], 0), BF16)
             bqk = self._hold(torch.cat([bq, bk], 0), torch.float32)
-            qk = self.conv([(a, Cc, 0, 1, False)], [(one, 0, 0, 0)], H, W, wqk, 2 * Cc, bias=bqk)
+            qk = self.conv([(a, Cc, 0, 1, False)], [(one, 0, 0, 0)], H, W, wqk, 2 * Cc, bias=bqk, want_stats=False)
             # V^T[b] = Wv . a[b]^T : weights are the A operand, the image is the B operand
             wv_img = self._hold(wv.reshape(1, 1, Cc, Cc), BF16)
             vT = self.conv([(wv_img, Cc, 0, 1, True)], [(one, 0, 0, 0)], 1, Cc, a.view(B, N, Cc), N,
@@ -273,11 +311,11 @@ class UNetPlan:
             self._op(self.L.its_softmax_rows, P.data_ptr(), S.data_ptr(), B * N, N, kind="softmax")
             bvh = self._hold(bv, torch.float32)
             o = self.conv([(P, N, 0, 1, False)], [(one, 0, 0, 0)], H, W, vT.view(B, Cc, N), Cc, bias=bvh,
-                          w_batch_stride=Cc * N)
+                          w_batch_stride=Cc * N, want_stats=False)
         else:
             wqkv = self._hold(torch.cat([wq, wk, wv], 0), BF16)
             bqkv = self._hold(torch.cat([bq, bk, bv], 0), torch.float32)
-            qkv = self.conv([(a, Cc, 0, 1, False)], [(one, 0, 0, 0)], H, W, wqkv, 3 * Cc, bias=bqkv)
+            qkv = self.conv([(a, Cc, 0, 1, False)], [(one, 0, 0, 0)], H, W, wqkv, 3 * Cc, bias=bqkv, want_stats=False)
             o = self._new((B, H, W, Cc))
             self._op(self.L.its_attention_small, o.data_ptr(), qkv.data_ptr(), B, N, Cc, scale,
                      flops=4 * B * N * N * Cc, kind="attention_small")
@@ -344,6 +382,7 @@ class UNetPlan:
         ch = m.head.out_channels
         self.gn_partials = None
         self.ws, self.split_k = None, True
+        self.stats_of, self.schedule, self.fold_residual = {}, 0, True
         self.x_in = self._new((self.n_img_in, 3, H, W), torch.float32)
         self.t_dev = torch.zeros(1, dtype=torch.int32, device=self.dev)
         self.t_idx = torch.zeros(B, dtype=torch.int64, device=self.dev)

@@ -171,7 +171,7 @@ def test_conv_head_and_tail(cuda_dev, built_lib):
 
 
 # -------------------------------------------------------------- tap-GEMM -----
-def _conv_case(dev, impl, B, H, Cin, Cout, *, k=3, stride=1, extras=False, seed=0):
+def _conv_case(dev, impl, B, H, Cin, Cout, *, k=3, stride=1, extras=False, seed=0, alpha=0.5):
     from its_b200.engine import UNetPlan, pack_conv_weight, taps_square
     g = torch.Generator().manual_seed(seed + 17 * B + H + Cin + Cout)
     x = torch.randn(B, Cin, H, H, generator=g).to(dev)
@@ -185,8 +185,8 @@ def _conv_case(dev, impl, B, H, Cin, Cout, *, k=3, stride=1, extras=False, seed=
         vec = torch.randn(B, Cout + 8, generator=g).to(dev)
         vec2 = torch.randn(1, Cout, generator=g).to(dev)
         res = torch.randn(B, Cout, Ho, Ho, generator=g).to(dev)
-        kw = dict(vec=vec, vec_off=8, vec2=vec2, res=nhwc(res), alpha=0.5)
-        ref = 0.5 * F.conv2d(bf(x), bf(w), None, stride=stride, padding=k // 2) + bias.view(1, -1, 1, 1) \
+        kw = dict(vec=vec, vec_off=8, vec2=vec2, res=nhwc(res), alpha=alpha)
+        ref = alpha * F.conv2d(bf(x), bf(w), None, stride=stride, padding=k // 2) + bias.view(1, -1, 1, 1) \
             + vec[:, 8:].view(B, Cout, 1, 1) + vec2.view(1, Cout, 1, 1) + bf(res)
     wp = pack_conv_weight(w).to(torch.bfloat16).contiguous()
     xin = nhwc(x)
@@ -219,6 +219,69 @@ def test_conv_igemm_vs_torch(cuda_dev, built_lib, impl, B, H, Cin, Cout, k, stri
     got, ref = _conv_case(cuda_dev, impl, B, H, Cin, Cout, k=k, stride=stride, extras=extras)
     check_close(got, ref, 6e-3, f"conv impl={impl}")
 
+
+
+@pytest.mark.parametrize("schedule", [1, 2], ids=["tile_per_cta", "persistent"])
+@pytest.mark.parametrize("B,H,Cin,Cout,k,stride,extras", CONV_SHAPES)
+def test_conv_igemm_schedules(cuda_dev, built_lib, schedule, B, H, Cin, Cout, k, stride, extras):
+    """Both tcgen05 schedules on every shape (the persistent one folds the residual as an identity tap)."""
+    from its_b200.engine import UNetPlan
+    orig = UNetPlan.scratch
+
+    def scratch(dev, n, impl=None):
+        p = orig(dev, n, impl)
+        p.schedule = schedule
+        p.split_k = schedule != 2
+        return p
+    UNetPlan.scratch = scratch
+    try:
+        got, ref = _conv_case(cuda_dev, 0, B, H, Cin, Cout, k=k, stride=stride, extras=extras,
+                             alpha=1.0 if schedule == 2 else 0.5)
+    finally:
+        UNetPlan.scratch = orig
+    check_close(got, ref, 6e-3, f"conv schedule={schedule}")
+
+
+@pytest.mark.parametrize("B,H,C0,C1,Cout", [(3, 32, 128, 0, 128), (2, 16, 256, 128, 256), (5, 8, 384, 256, 384),
+                                            (9, 4, 512, 512, 512), (2, 64, 128, 0, 128)])
+def test_persistent_conv_statistics_feed_group_norm(cuda_dev, built_lib, B, H, C0, C1, Cout):
+    """The persistent tap-GEMM leaves per-(image, 4 channels, tile) sums of the stored bf16 tensor;
+    GroupNorm of (that tensor | a second such tensor) through its_group_norm_apply must match
+    nn.GroupNorm on the stored values (Model.py:170-173 after Model.py:279-280's concat)."""
+    from its_b200.engine import UNetPlan, pack_conv_weight, taps_square
+    g = torch.Generator().manual_seed(B + H + C0 + C1)
+    plan = UNetPlan.scratch(cuda_dev, B, 0)
+    plan.split_k = False
+    plan.schedule = 2
+    keep, outs = [], []
+    for C in [c for c in (C0, C1) if c]:
+        x = (torch.randn(B, 64, H, H, generator=g) * 1.5 + 0.3).to(cuda_dev)
+        w = (torch.randn(C, 64, 3, 3, generator=g) / 24).to(cuda_dev)
+        bias = torch.randn(C, generator=g).to(cuda_dev)
+        xin, wp = nhwc(x), pack_conv_weight(w).to(torch.bfloat16).contiguous()
+        keep += [xin, wp, bias]
+        outs.append(plan.conv([(xin, 64, 0, 1, False)], [(taps_square(3), 0, 0, 0)], H, H, wp, C, bias=bias))
+    gn = torch.nn.GroupNorm(32, C0 + C1).to(cuda_dev)
+    with torch.no_grad():
+        gn.weight.copy_(1 + 0.2 * torch.randn(C0 + C1, generator=g))
+        gn.bias.copy_(0.1 * torch.randn(C0 + C1, generator=g))
+    y = plan.group_norm(outs, gn, True)
+    assert plan.op_info[-1][0] == "group_norm_apply"
+    plan.run()
+    torch.cuda.synchronize()
+    # the partial sums are sums of the stored values
+    for o in outs:
+        st, parts = plan.stats_of[o.data_ptr()]
+        v = o.float()
+        C = v.shape[-1]
+        ref_s = v.reshape(B, -1, C // 4, 4).sum((1, 3))
+        ref_q = (v * v).reshape(B, -1, C // 4, 4).sum((1, 3))
+        assert (st[..., 0].sum(1) - ref_s).abs().max().item() <= 2e-3 * max(1.0, ref_s.abs().max().item())
+        assert (st[..., 1].sum(1) - ref_q).abs().max().item() <= 2e-4 * ref_q.abs().max().item()
+    with torch.no_grad():
+        ref = gn(torch.cat([nchw(o) for o in outs], 1))
+        ref = ref * torch.sigmoid(ref)
+    check_close(nchw(y), ref, 6e-3, "group_norm_apply")
 
 @pytest.mark.parametrize("impl", [1, 0], ids=["cudacore", "tcgen05"])
 def test_conv_fused_shortcut_three_sources(cuda_dev, built_lib, impl):
