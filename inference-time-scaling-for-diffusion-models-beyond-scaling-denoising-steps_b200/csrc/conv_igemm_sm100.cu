@@ -454,6 +454,10 @@ int tapgemm_launch_sm100(const its_conv_desc* d, const TapGemmParams& p, cudaStr
   ITS_REQUIRE(bn == 32 || bn == 64 || bn == 128 || bn == 192 || bn == 256, "its_conv_igemm: bn=%d", bn);
   ITS_REQUIRE(p.out_nchw || p.Cout % 8 == 0, "its_conv_igemm: Cout=%d must be a multiple of 8", p.Cout);
   ITS_REQUIRE(p.splits == 1 || (!p.out_nchw && p.Cout % 8 == 0), "its_conv_igemm: split-K needs NHWC output");
+  if (p.splits > 1) {
+    const long long need = (long long)p.nphases * p.splits * p.B * p.Hm * p.Wm * p.Cout;
+    ITS_REQUIRE(d->ws_elems >= need, "its_conv_igemm: workspace has %lld floats, %lld needed", (long long)d->ws_elems, need);
+  }
   for (int f = 0; f < p.nphases; ++f)
     ITS_REQUIRE(p.splits <= p.phase[f].nkb, "its_conv_igemm: splits=%d exceeds the %d k-blocks of phase %d", p.splits, p.phase[f].nkb, f);
   ITS_REQUIRE(p.w_pitch % 8 == 0 && p.w_batch_stride % 8 == 0, "its_conv_igemm: weight pitch alignment");

@@ -68,6 +68,30 @@ __device__ __forceinline__ TileCoord decode_tile(const TapGemmParams& p, int til
   return c;
 }
 
+// Split-K work items: item w of total_tiles * S.  All partial items (split s < S-1) come first,
+// the owner items (s = S-1, which reduce and run the epilogue) last, so that with the static
+// round-robin schedule an owner never waits for work queued behind another waiting owner.
+struct WorkItem {
+  int tile, split;
+};
+__device__ __forceinline__ WorkItem decode_item(int w, int total_tiles, int S) {
+  WorkItem it;
+  if (S == 1) {
+    it.tile = w;
+    it.split = 0;
+  } else {
+    const int npart = total_tiles * (S - 1);
+    if (w < npart) {
+      it.tile = w / (S - 1);
+      it.split = w - it.tile * (S - 1);
+    } else {
+      it.tile = w - npart;
+      it.split = S - 1;
+    }
+  }
+  return it;
+}
+
 template <int BN, int STAGES, int MT>
 __global__ void __launch_bounds__(P_THREADS, 1)
 tapgemm_persist_kernel(const __grid_constant__ TapGemmParams p, const __grid_constant__ CUtensorMap tmA0,
@@ -92,6 +116,8 @@ tapgemm_persist_kernel(const __grid_constant__ TapGemmParams p, const __grid_con
   const int tiles_m = p.tiles_x * (p.tiles_y / MT) * p.tiles_b;
   const int tiles_n = (p.Cout + BN - 1) / BN;
   const int total_tiles = tiles_m * tiles_n * p.nphases;
+  const int S = p.splits;
+  const int total_items = total_tiles * S;
 
   long long* dbg = nullptr;
   if (p.dbg != nullptr) {
@@ -140,64 +166,73 @@ tapgemm_persist_kernel(const __grid_constant__ TapGemmParams p, const __grid_con
 
   if (warp == 0) {
     // ------------------------------------------------ TMA producer ----
-    if (lane == 0) {
-      uint32_t it = 0;   // k-blocks issued so far (ring position)
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const TileCoord c = decode_tile(p, tile, tiles_m, tiles_n, BN, MT);
-        const DevPhase& ph = p.phase[c.phase];
-        int g = 0;
-        for (int t = 0; t < ph.ntaps; ++t) {
-          const int si = ph.src[t];
-          const DevSrc& s = p.src[si];
-          const int ncb = s.C / BK;
-          const CUtensorMap* tm = (si == 0) ? &tmA0 : (si == 1) ? &tmA1 : &tmA2;
-          const int cx = c.tx * p.bw * s.stride + ph.dx[t];
-          const int cy = c.ty * (p.bh * MT) * s.stride + ph.dy[t];
-          const int cb_img = s.bcast ? 0 : c.tb * p.bb;
-          for (int cb = 0; cb < ncb; ++cb, ++g, ++it) {
-            const uint32_t stage = it % STAGES;
-            const uint32_t parity = (it / STAGES) & 1u;
-            mbar_wait(&empty_bar[stage], parity ^ 1u);
+    // converged warp; one elected lane issues the loads of a stage
+    uint32_t it = 0;   // k-blocks issued so far (ring position)
+    for (int w = blockIdx.x; w < total_items; w += gridDim.x) {
+      const WorkItem wi = decode_item(w, total_tiles, S);
+      const TileCoord c = decode_tile(p, wi.tile, tiles_m, tiles_n, BN, MT);
+      const DevPhase& ph = p.phase[c.phase];
+      const int kb0 = (ph.nkb * wi.split) / S, kb1 = (ph.nkb * (wi.split + 1)) / S;
+      int g = 0;
+      for (int t = 0; t < ph.ntaps && g < kb1; ++t) {
+        const int si = ph.src[t];
+        const DevSrc& s = p.src[si];
+        const int ncb = s.C / BK;
+        if (g + ncb <= kb0) { g += ncb; continue; }
+        const CUtensorMap* tm = (si == 0) ? &tmA0 : (si == 1) ? &tmA1 : &tmA2;
+        const int cx = c.tx * p.bw * s.stride + ph.dx[t];
+        const int cy = c.ty * (p.bh * MT) * s.stride + ph.dy[t];
+        const int cb_img = s.bcast ? 0 : c.tb * p.bb;
+        for (int cb = 0; cb < ncb; ++cb, ++g) {
+          if (g < kb0 || g >= kb1) continue;
+          const uint32_t stage = it % STAGES;
+          const uint32_t parity = (it / STAGES) & 1u;
+          mbar_wait(&empty_bar[stage], parity ^ 1u);
+          if (elect_one_sync()) {
             uint8_t* a_dst = smem + stage * L::STAGE_BYTES;
             mbar_expect_tx(&full_bar[stage], (uint32_t)L::STAGE_BYTES);
             tma_load_4d(a_dst, tm, &full_bar[stage], cb * BK, cx, cy, cb_img);
             tma_load_3d(a_dst + MT * A_BYTES, &tmB, &full_bar[stage], ph.w_k0 + g * BK, c.n0, 0);
           }
+          __syncwarp();
+          ++it;
         }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------- MMA issuer -----
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(BN);
-      uint32_t it = 0, j = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++j) {
-        const int phase_idx = tile / (tiles_m * tiles_n);
-        const int nkb = p.phase[phase_idx].nkb;
-        const uint32_t buf = j & 1u;
-        mbar_wait(&tempty_bar[buf], ((j >> 1) & 1u) ^ 1u);   // epilogue has drained this buffer
+    // the whole warp walks the loop (converged waits), one elected lane issues
+    constexpr uint32_t idesc = make_idesc(BN);
+    uint32_t it = 0, j = 0;
+    for (int w = blockIdx.x; w < total_items; w += gridDim.x, ++j) {
+      const WorkItem wi = decode_item(w, total_tiles, S);
+      const int nkb_phase = p.phase[wi.tile / (tiles_m * tiles_n)].nkb;
+      const int nkb = (nkb_phase * (wi.split + 1)) / S - (nkb_phase * wi.split) / S;
+      const uint32_t buf = j & 1u;
+      mbar_wait(&tempty_bar[buf], ((j >> 1) & 1u) ^ 1u);   // epilogue has drained this buffer
+      tcgen05_fence_after();
+      const uint32_t d_tmem = tmem_base + buf * (MT * BN);
+      for (int kb = 0; kb < nkb; ++kb, ++it) {
+        const uint32_t stage = it % STAGES;
+        const uint32_t parity = (it / STAGES) & 1u;
+        mbar_wait(&full_bar[stage], parity);
         tcgen05_fence_after();
-        const uint32_t d_tmem = tmem_base + buf * (MT * BN);
-        for (int kb = 0; kb < nkb; ++kb, ++it) {
-          const uint32_t stage = it % STAGES;
-          const uint32_t parity = (it / STAGES) & 1u;
-          mbar_wait(&full_bar[stage], parity);
-          tcgen05_fence_after();
+        if (elect_one_sync()) {
           const uint32_t a_addr = smem_u32(smem + stage * L::STAGE_BYTES);
           const uint64_t bdesc = make_smem_desc(a_addr + MT * A_BYTES);
 #pragma unroll
           for (int m = 0; m < MT; ++m) {
             const uint64_t adesc = make_smem_desc(a_addr + m * A_BYTES);
 #pragma unroll
-            for (int k = 0; k < BK / 16; ++k)
-              umma_bf16(d_tmem + m * BN, adesc + 2 * k, bdesc + 2 * k, idesc, (uint32_t)((kb | k) != 0));
+            for (int k2 = 0; k2 < BK / 16; ++k2)
+              umma_bf16(d_tmem + m * BN, adesc + 2 * k2, bdesc + 2 * k2, idesc, (uint32_t)((kb | k2) != 0));
           }
           umma_commit(&empty_bar[stage]);
+          if (kb == nkb - 1) umma_commit(&tfull_bar[buf]);
         }
-        umma_commit(&tfull_bar[buf]);
+        __syncwarp();
       }
     }
-    __syncwarp();
   } else if (warp < 10) {
     // --------------------------------------------------- epilogue -----
     // 8 warps: warp w reads TMEM lane quarter w % 4 (rows 32q..32q+31 of the sub-tile) and
@@ -216,14 +251,62 @@ tapgemm_persist_kernel(const __grid_constant__ TapGemmParams p, const __grid_con
     const int st_ch = et & 15, st_ib = et >> 4; // final reduce role: 4-channel chunk, image in sub-tile
     float2* prev_dst = nullptr;                 // deferred final reduce of the previous panel
     uint32_t j = 0, pc = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++j) {
-      const TileCoord c = decode_tile(p, tile, tiles_m, tiles_n, BN, MT);
+    for (int w = blockIdx.x; w < total_items; w += gridDim.x, ++j) {
+      const WorkItem wi = decode_item(w, total_tiles, S);
+      const TileCoord c = decode_tile(p, wi.tile, tiles_m, tiles_n, BN, MT);
       const uint32_t buf = j & 1u;
+      constexpr int NPANEL = BN / PANEL_COLS;
+      if (S > 1) {
+        int* flags = reinterpret_cast<int*>(p.ws);
+        float* parts = p.ws + p.ws_flag_words;
+        if (wi.split < S - 1) {
+          // partial item: raw fp32 accumulators -> workspace row (128-byte runs per thread), then
+          // publish.  No TMA stores, no statistics.
+          mbar_wait(&tfull_bar[buf], (j >> 1) & 1u);
+          tcgen05_fence_after();
+          float* wsrow = parts + ((long long)(wi.tile * (S - 1) + wi.split) * BM + row) * BN + half * 32;
+#pragma unroll 1
+          for (int pn = 0; pn < NPANEL; ++pn) {
+            uint32_t v[32];
+            tmem_ld32_nowait(tmem_base + ((uint32_t)(q * 32) << 16) + buf * (MT * BN) +
+                                 (uint32_t)(pn * PANEL_COLS + half * 32), v);
+            tmem_wait_ld();
+            float4* dst = reinterpret_cast<float4*>(wsrow + pn * PANEL_COLS);
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              __stcg(dst + i, make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
+                                          __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3])));
+          }
+          tcgen05_fence_before();
+          mbar_arrive(&tempty_bar[buf]);
+          __threadfence();
+          named_bar_sync(1, P_EPI_THREADS);
+          if (et == 0) {
+            int* f = flags + wi.tile * (S - 1) + wi.split;
+            asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(f), "r"(1) : "memory");
+          }
+          continue;
+        }
+        // owner item: wait until every partial of this tile has been published
+        if (et == 0) {
+          for (int sp = 0; sp < S - 1; ++sp) {
+            int* f = flags + wi.tile * (S - 1) + sp;
+            int seen = 0;
+            for (uint32_t spin = 0; spin < (1u << 24); ++spin) {
+              asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(f) : "memory");
+              if (seen != 0) break;
+              __nanosleep(64);
+            }
+            if (seen == 0) __trap();     // a lost partial would otherwise hang the device
+            *f = 0;                      // self-cleaning: the next launch finds the flags zeroed
+          }
+        }
+        named_bar_sync(1, P_EPI_THREADS);
+      }
       int b = c.tb * p.bb + rb;
       if (b >= p.B) b = p.B - 1;         // rows of a ragged last tile: values are never stored
       const float* vrow = p.vec ? p.vec + (long long)b * p.vec_stride : nullptr;
       const float* vrow2 = p.vec2 ? p.vec2 + (long long)b * p.vec2_stride : nullptr;
-      constexpr int NPANEL = BN / PANEL_COLS;
 #pragma unroll 1
       for (int pi = 0; pi < MT * NPANEL; ++pi, ++pc) {
         const int m = pi / NPANEL, pn = pi - m * NPANEL;
@@ -271,6 +354,26 @@ tapgemm_persist_kernel(const __grid_constant__ TapGemmParams p, const __grid_con
         if (pi == MT * NPANEL - 1) {     // accumulators fully read: hand the buffer back to the MMA warp
           tcgen05_fence_before();
           mbar_arrive(&tempty_bar[buf]);
+        }
+        if (S > 1) {
+          // fixed summation order: partial 0 + partial 1 + ... + own K range
+          const float* prow = p.ws + p.ws_flag_words +
+                              ((long long)(wi.tile * (S - 1)) * BM + row) * BN + pn * PANEL_COLS + half * 32;
+          float acc[32];
+          for (int sp = 0; sp < S - 1; ++sp) {
+            const float4* src = reinterpret_cast<const float4*>(prow + (long long)sp * BM * BN);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 t4 = __ldcg(src + i);
+              if (sp == 0) {
+                acc[4 * i] = t4.x; acc[4 * i + 1] = t4.y; acc[4 * i + 2] = t4.z; acc[4 * i + 3] = t4.w;
+              } else {
+                acc[4 * i] += t4.x; acc[4 * i + 1] += t4.y; acc[4 * i + 2] += t4.z; acc[4 * i + 3] += t4.w;
+              }
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(acc[i] + __uint_as_float(v[i]));
         }
         const uint32_t row_addr = smem_u32(sbuf) + (uint32_t)row * 128u;
 #pragma unroll
@@ -345,8 +448,10 @@ tapgemm_persist_kernel(const __grid_constant__ TapGemmParams p, const __grid_con
     if (lane == 0) {
       uint32_t pc = 0;
       constexpr int NPANEL = BN / PANEL_COLS;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const TileCoord c = decode_tile(p, tile, tiles_m, tiles_n, BN, MT);
+      for (int w = blockIdx.x; w < total_items; w += gridDim.x) {
+        const WorkItem wi = decode_item(w, total_tiles, S);
+        if (wi.split < S - 1) continue;          // partial items store nothing
+        const TileCoord c = decode_tile(p, wi.tile, tiles_m, tiles_n, BN, MT);
         const DevPhase& ph = p.phase[c.phase];
         for (int pi = 0; pi < MT * NPANEL; ++pi, ++pc) {
           const int m = pi / NPANEL, pn = pi - m * NPANEL;
@@ -400,7 +505,7 @@ static int persist_bn(const its_conv_desc* d, const TapGemmParams& p) {
 }
 
 bool tapgemm_persist_eligible(const its_conv_desc* d, const TapGemmParams& p) {
-  if (p.out_fp32 || p.out_nchw || p.splits > 1 || p.w_batch_stride != 0 || p.res != nullptr) return false;
+  if (p.out_fp32 || p.out_nchw || p.w_batch_stride != 0 || p.res != nullptr) return false;
   if (p.Cout % 64 != 0 || p.out_c_pitch % 8 != 0) return false;
   const int bn = persist_bn(d, p);
   if (!(bn == 64 || bn == 128 || bn == 192 || bn == 256) || p.Cout % bn != 0) return false;
@@ -422,7 +527,7 @@ static int launch_persist(const TapGemmParams& p, const CUtensorMap* tmA, const 
     ITS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
     configured = true;
   }
-  const int tiles = p.tiles_x * (p.tiles_y / MT) * p.tiles_b * (p.Cout / BN) * p.nphases;
+  const int tiles = p.tiles_x * (p.tiles_y / MT) * p.tiles_b * (p.Cout / BN) * p.nphases * p.splits;
   const int sms = device_sm_count();
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(tiles < sms ? tiles : sms, 1, 1);
@@ -448,7 +553,21 @@ int tapgemm_launch_persist(const its_conv_desc* d, const TapGemmParams& p, cudaS
                 p.stats_parts, tapgemm_stats_parts(p));
   // two row boxes per tile (shared weight tiles) when the N tile leaves TMEM room for two
   // double-buffered accumulators and a tile of 2 x bh rows still tiles the image
-  const int mt = (bn <= 128 && p.bb == 1 && p.tiles_y % 2 == 0 && d->cluster != 1) ? 2 : 1;
+  const int mt = (bn <= 128 && p.bb == 1 && p.tiles_y % 2 == 0 && d->cluster != 1 && p.splits == 1) ? 2 : 1;
+  TapGemmParams pp = p;
+  if (p.splits > 1) {
+    // workspace: [flags: one int per (tile, partial split), padded to 64 words][partials fp32]
+    const long long tiles = (long long)p.tiles_x * p.tiles_y * p.tiles_b * (p.Cout / bn) * p.nphases;
+    const long long nflag = ((tiles * (p.splits - 1) + 63) / 64) * 64;
+    const long long need = nflag + tiles * (p.splits - 1) * BM * bn;
+    ITS_REQUIRE(d->ws != nullptr && d->ws_elems >= need,
+                "its_conv_igemm: persistent split-K workspace has %lld floats, %lld needed (must be zero-initialised)",
+                (long long)d->ws_elems, need);
+    for (int f = 0; f < p.nphases; ++f)
+      ITS_REQUIRE(p.splits <= p.phase[f].nkb, "its_conv_igemm: splits=%d exceeds the %d k-blocks of phase %d", p.splits, p.phase[f].nkb, f);
+    ITS_REQUIRE(tiles * p.splits <= device_sm_count(), "its_conv_igemm: %lld split-K work items exceed the %d resident CTAs", tiles * p.splits, device_sm_count());
+    pp.ws_flag_words = (int)nflag;
+  }
   CUtensorMap tmA[ITS_MAX_SRC], tmB, tmOut;
   int rc = tapgemm_encode_operand_maps(p, bn, tmA, &tmB, mt);
   if (rc != ITS_OK) return rc;
@@ -472,14 +591,14 @@ int tapgemm_launch_persist(const its_conv_desc* d, const TapGemmParams& p, cudaS
   }
   if (rc != ITS_OK) return rc;
   if (mt == 2) {
-    if (bn == 64) return launch_persist<64, 4, 2>(p, tmA, tmB, tmOut, stream);
-    return launch_persist<128, 4, 2>(p, tmA, tmB, tmOut, stream);
+    if (bn == 64) return launch_persist<64, 4, 2>(pp, tmA, tmB, tmOut, stream);
+    return launch_persist<128, 4, 2>(pp, tmA, tmB, tmOut, stream);
   }
   switch (bn) {
-    case 64:  return launch_persist<64, 6, 1>(p, tmA, tmB, tmOut, stream);
-    case 128: return launch_persist<128, 5, 1>(p, tmA, tmB, tmOut, stream);
-    case 192: return launch_persist<192, 4, 1>(p, tmA, tmB, tmOut, stream);
-    default:  return launch_persist<256, 4, 1>(p, tmA, tmB, tmOut, stream);
+    case 64:  return launch_persist<64, 8, 1>(pp, tmA, tmB, tmOut, stream);
+    case 128: return launch_persist<128, 6, 1>(pp, tmA, tmB, tmOut, stream);
+    case 192: return launch_persist<192, 4, 1>(pp, tmA, tmB, tmOut, stream);
+    default:  return launch_persist<256, 4, 1>(pp, tmA, tmB, tmOut, stream);
   }
 }
 

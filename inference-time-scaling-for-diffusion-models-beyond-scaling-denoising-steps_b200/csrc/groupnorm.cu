@@ -260,14 +260,40 @@ struct GnStatArgs {
 };
 
 __global__ void __launch_bounds__(GN_THREADS) gn_apply_stats_kernel(const GnStatArgs a) {
-  pdl_prologue();
   __shared__ float s_mean[64], s_rstd[64];
-  __shared__ float2 s_ab[8 * GN_MAX_VEC];
   const int tid = threadIdx.x;
   const int chunk = blockIdx.x, img = blockIdx.y;
   const int cg = a.C / a.groups;         // channels per group (multiple of 4)
   const int cg4 = cg >> 2;
   const int tpg = GN_THREADS / a.groups; // lanes per group: power of two, <= 32
+  const int nvec = a.C / 8;
+  const int prow = GN_THREADS / nvec;
+  const int cv = tid % nvec, pl = tid / nvec;
+  const bool active = pl < prow;
+  const int per = (a.HW + a.chunks - 1) / a.chunks;
+  const int p0 = chunk * per, p1 = min(a.HW, p0 + per);
+  const bool from0 = cv * 8 < a.C0;
+  const __nv_bfloat16* sp = from0 ? a.src0 + cv * 8 : a.src1 + (cv * 8 - a.C0);
+  const int spitch = from0 ? a.C0 : a.C1;
+  constexpr int U = 4;                   // independent 16-byte loads in flight per thread
+  pdl_prologue();
+  // first batch of activations and the affine parameters are requested before the
+  // statistics chain below, so the two global round trips overlap
+  bf16x8 raw[U];
+  float gam[8], bet[8];
+  if (active) {
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int p = p0 + pl + u * prow;
+      if (p < p1) raw[u] = *reinterpret_cast<const bf16x8*>(sp + ((long long)img * a.HW + p) * spitch);
+    }
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(a.gamma + cv * 8));
+    const float4 g1 = __ldg(reinterpret_cast<const float4*>(a.gamma + cv * 8) + 1);
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(a.beta + cv * 8));
+    const float4 b1 = __ldg(reinterpret_cast<const float4*>(a.beta + cv * 8) + 1);
+    gam[0] = g0.x; gam[1] = g0.y; gam[2] = g0.z; gam[3] = g0.w; gam[4] = g1.x; gam[5] = g1.y; gam[6] = g1.z; gam[7] = g1.w;
+    bet[0] = b0.x; bet[1] = b0.y; bet[2] = b0.z; bet[3] = b0.w; bet[4] = b1.x; bet[5] = b1.y; bet[6] = b1.z; bet[7] = b1.w;
+  }
   {
     const int g = tid / tpg, l = tid - g * tpg;
     double s = 0.0, q = 0.0;
@@ -299,35 +325,21 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_stats_kernel(const GnStat
     }
   }
   __syncthreads();
-  for (int c = tid; c < a.C; c += GN_THREADS) {
-    const int g = c / cg;
-    const float sc = s_rstd[g] * __ldg(a.gamma + c);
-    s_ab[c] = make_float2(sc, __ldg(a.beta + c) - s_mean[g] * sc);
-  }
-  __syncthreads();
-  const int nvec = a.C / 8;
-  const int prow = GN_THREADS / nvec;
-  const int cv = tid % nvec, pl = tid / nvec;
-  if (pl >= prow) return;
+  if (!active) return;
   float scale[8], shift[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    const float2 ab = s_ab[cv * 8 + i];
-    scale[i] = ab.x;
-    shift[i] = ab.y;
+    const int g = (cv * 8 + i) / cg;
+    scale[i] = s_rstd[g] * gam[i];
+    shift[i] = bet[i] - s_mean[g] * scale[i];
   }
-  const int per = (a.HW + a.chunks - 1) / a.chunks;
-  const int p0 = chunk * per, p1 = min(a.HW, p0 + per);
-  const bool from0 = cv * 8 < a.C0;
-  const __nv_bfloat16* sp = from0 ? a.src0 + cv * 8 : a.src1 + (cv * 8 - a.C0);
-  const int spitch = from0 ? a.C0 : a.C1;
-  constexpr int U = 4;                   // independent 16-byte loads in flight per thread
   for (int pb = p0 + pl; pb < p1; pb += prow * U) {
-    bf16x8 raw[U];
+    if (pb != p0 + pl) {
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int p = pb + u * prow;
-      if (p < p1) raw[u] = *reinterpret_cast<const bf16x8*>(sp + ((long long)img * a.HW + p) * spitch);
+      for (int u = 0; u < U; ++u) {
+        const int p = pb + u * prow;
+        if (p < p1) raw[u] = *reinterpret_cast<const bf16x8*>(sp + ((long long)img * a.HW + p) * spitch);
+      }
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
@@ -338,7 +350,7 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_stats_kernel(const GnStat
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const float v = fmaf(f[i], scale[i], shift[i]);
-          f[i] = a.silu ? silu_f(v) : v;
+          f[i] = a.silu ? silu_fast(v) : v;
         }
         *reinterpret_cast<bf16x8*>(a.out + ((long long)img * a.HW + p) * a.C + cv * 8) = pack8(f);
       }

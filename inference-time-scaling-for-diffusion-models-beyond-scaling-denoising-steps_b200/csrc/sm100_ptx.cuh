@@ -140,6 +140,19 @@ __host__ __device__ constexpr uint32_t make_idesc(int bn) {
 __host__ __device__ constexpr int tmem_cols_for(int bn) { return bn <= 32 ? 32 : bn <= 64 ? 64 : bn <= 128 ? 128 : 256; }
 
 
+// one lane of a fully converged warp (the compiler keeps the uniform datapath for code
+// predicated on it, instead of serialising over the active lanes)
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "elect.sync _|P1, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P1;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
 // ---- additions used by the persistent kernels ---------------------------------------
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");

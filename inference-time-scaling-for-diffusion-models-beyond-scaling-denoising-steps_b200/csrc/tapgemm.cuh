@@ -38,7 +38,9 @@ struct TapGemmParams {
   float alpha;
   int out_nchw;
   int splits;                // split-K factor (>= 1)
-  float* ws;                 // [nphases][splits][B*Hm*Wm][Cout] fp32 partial sums
+  float* ws;                 // [nphases][splits][B*Hm*Wm][Cout] fp32 partial sums (tile-per-CTA schedule);
+                             // persistent schedule: [flags][tile][split][128][BN]
+  int ws_flag_words;         // persistent split-K: ints reserved for the flags at the head of ws
   long long* dbg;            // optional per-CTA clock stamps (diagnostics)
   float* stats;              // GroupNorm partial sums [B][stats_parts][Cout/4][2] or null (persistent kernel)
   int stats_parts;

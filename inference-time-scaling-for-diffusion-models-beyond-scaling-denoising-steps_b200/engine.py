@@ -81,6 +81,7 @@ class UNetPlan:
         self.gn_partials, self.tproj, self.cproj = None, None, None
         self.ws, self.split_k = None, True
         self.stats_of, self.schedule, self.fold_residual = {}, 0, True
+        self.ws_persist, self.sm_count = None, 148
         return self
 
     # ------------------------------------------------------------ buffers --
@@ -133,6 +134,49 @@ class UNetPlan:
         s = min(148 // ctas, nkb_min // 4, 16)
         return max(1, s)
 
+    @staticmethod
+    def _box(Hm: int, Wm: int) -> Tuple[int, int, int]:
+        bw = min(Wm, 128)
+        bh = min(Hm, 128 // bw)
+        return bw, bh, 128 // (bw * bh)
+
+    def _tiles_at(self, B: int, Hm: int, Wm: int) -> int:
+        bw, bh, bb = self._box(Hm, Wm)
+        return -(-Wm // bw) * -(-Hm // bh) * -(-B // bb)
+
+    # Measured cost (ns) of one 64-deep k-block of a 128-row box on the persistent schedule
+    # (scripts/split_probe.py, scripts/tma_box_probe.py): the TMA unit delivers ~0.6 128-byte rows
+    # per clock, so narrow N tiles are operand-rate-bound, only the 256-wide one is tensor-bound.
+    _T_KB = {256: 290.0, 192: 250.0, 128: 215.0, 64: 175.0}
+    _T_SPLIT2 = 5000.0      # publish + re-read of the fp32 partial through L2, flag round trip
+
+    def _persist_plan(self, Hm, Wm, cout, nphases, nkb) -> Tuple[int, int]:
+        """(N tile, split-K factor) of a layer on the persistent schedule, from the layer shape at the
+        design batch only (so that the fp32 summation order never depends on the actual batch)."""
+        bw, bh, bb = self._box(Hm, Wm)
+        tiles_y = -(-Hm // bh)
+        tiles_m = self._tiles_at(self.DESIGN_BATCH, Hm, Wm)
+        best = None
+        for bn in (256, 192, 128, 64):
+            if cout % bn:
+                continue
+            tiles = tiles_m * (cout // bn) * nphases
+            two_rows = bn <= 128 and bb == 1 and tiles_y % 2 == 0
+            for S in (1, 2):
+                if S > 1 and (bn != 64 or nkb < 16 or tiles * S > self.sm_count or two_rows):
+                    break
+                if two_rows:                # two row boxes share each weight tile (measured ~410 ns per pair)
+                    rounds = -(-(tiles // 2) // self.sm_count)
+                    t = rounds * nkb * 410.0
+                else:
+                    rounds = -(-(tiles * S) // self.sm_count)
+                    t = rounds * -(-nkb // S) * self._T_KB[bn]
+                if S > 1:
+                    t += self._T_SPLIT2
+                if best is None or t < best[0] - 1e-9:
+                    best = (t, bn, S)
+        return best[1], best[2]
+
     def conv(self, srcs, phases, Hm, Wm, w, cout, *, out=None, out_scale=1, bias=None, vec=None,
              vec_off=0, vec2=None, vec2_off=0, res=None, alpha=1.0, out_fp32=False, w_batch_stride=0,
              w_pitch=None, B=None, out_shape=None, out_nchw=False, want_stats=True) -> torch.Tensor:
@@ -171,40 +215,61 @@ class UNetPlan:
         d.schedule = self.schedule
         impl = self._impl_for([s[1] for s in srcs], cout, out_nchw)
         launches = 1
-        if impl == 0 and not out_nchw and self.split_k:
-            nkb_min = min(sum(srcs[si][1] for si, _, _ in taps) // 64 for taps, _, _, _ in phases)
-            splits = self._splits_for(B, Hm, Wm, cout, len(phases), nkb_min, bool(w_batch_stride))
-            if splits > 1:
-                need = len(phases) * splits * B * Hm * Wm * cout
-                if self.ws is None or self.ws.numel() < need:
-                    self.ws = self._new((need,), torch.float32)
-                d.splits, d.ws, d.ws_elems = splits, self.ws.data_ptr(), self.ws.numel()
-                launches = 2
-        if (res is not None and impl == 0 and d.splits <= 1 and self.fold_residual and self.schedule != 1
-                and len(phases) == 1 and alpha == 1.0 and not out_fp32 and not out_nchw and not w_batch_stride
-                and len(srcs) < _lib.MAX_SRC and cout % 64 == 0 and res.shape[-1] == cout
-                and (w_pitch or w.shape[-1]) == w.shape[-1] and w.dim() == 2):
-            # identity shortcut as one more K block with identity weights (exact: 1.0 * bf16 value in
-            # the fp32 accumulator), so the layer runs on the persistent schedule, which has no
-            # residual read in its epilogue
-            k_used = sum(srcs[si][1] for si, _, _ in phases[0][0])
-            w = self._hold(torch.cat([w[:, :k_used].float(), torch.eye(cout, device=w.device)], 1), BF16)
-            i = d.nsrc
-            sN = d.src[i]
-            sN.ptr, sN.c_pitch, sN.c_off, sN.C = res.data_ptr(), res.shape[-1], 0, cout
-            sN.H, sN.W, sN.stride, sN.bcast = res.shape[1], res.shape[2], 1, 0
-            d.nsrc = i + 1
-            ph = d.phase[0]
-            ph.src[ph.ntaps], ph.dy[ph.ntaps], ph.dx[ph.ntaps] = i, 0, 0
-            ph.ntaps += 1
-            d.w, d.w_pitch = w.data_ptr(), w.shape[-1]
+        nkb_min = min(sum(srcs[si][1] for si, _, _ in taps) // 64 for taps, _, _, _ in phases)
+        can_fold = (res is not None and impl == 0 and self.fold_residual and self.schedule != 1
+                    and len(phases) == 1 and alpha == 1.0 and not out_fp32 and not out_nchw and not w_batch_stride
+                    and len(srcs) < _lib.MAX_SRC and cout % 64 == 0 and res.shape[-1] == cout
+                    and (w_pitch or w.shape[-1]) == w.shape[-1] and w.dim() == 2)
+        if can_fold:
             d.res = None
-        if impl == 0 and want_stats:
-            parts = self.L.its_conv_stats_parts(C.byref(d))
-            if parts > 0:
+        persistent = impl == 0 and self.L.its_conv_stats_parts(C.byref(d)) > 0
+        bn, splits = 0, 1
+        if persistent and self.split_k:
+            bn, splits = self._persist_plan(Hm, Wm, cout, len(phases), nkb_min + (cout // 64 if can_fold else 0))
+            if splits > 1 and self._tiles_at(B, Hm, Wm) * (cout // bn) * len(phases) * splits > self.sm_count:
+                persistent = False          # more split-K work items than resident CTAs at this batch
+        if persistent:
+            if can_fold:
+                # identity shortcut as one more K block with identity weights (exact: 1.0 * bf16 value
+                # in the fp32 accumulator): the persistent schedule has no residual read in its epilogue
+                k_used = sum(srcs[si][1] for si, _, _ in phases[0][0])
+                w = self._hold(torch.cat([w[:, :k_used].float(), torch.eye(cout, device=w.device)], 1), BF16)
+                i = d.nsrc
+                sN = d.src[i]
+                sN.ptr, sN.c_pitch, sN.c_off, sN.C = res.data_ptr(), res.shape[-1], 0, cout
+                sN.H, sN.W, sN.stride, sN.bcast = res.shape[1], res.shape[2], 1, 0
+                d.nsrc = i + 1
+                ph = d.phase[0]
+                ph.src[ph.ntaps], ph.dy[ph.ntaps], ph.dx[ph.ntaps] = i, 0, 0
+                ph.ntaps += 1
+                d.w, d.w_pitch = w.data_ptr(), w.shape[-1]
+            d.bn = bn
+            if splits > 1:
+                tiles = self._tiles_at(B, Hm, Wm) * (cout // bn) * len(phases)
+                nflag = -(-(tiles * (splits - 1)) // 64) * 64
+                need = nflag + tiles * (splits - 1) * 128 * bn
+                if self.ws_persist is None or self.ws_persist.numel() < need:
+                    # flags at the head must start out zero; the kernel leaves them zero again
+                    self.ws_persist = torch.zeros(need, dtype=torch.float32, device=self.dev)
+                    self.keep.append(self.ws_persist)
+                d.splits, d.ws, d.ws_elems = splits, self.ws_persist.data_ptr(), self.ws_persist.numel()
+            if want_stats:
+                parts = self.L.its_conv_stats_parts(C.byref(d))
                 st = self._new((B, parts, cout // 4, 2), torch.float32)
                 d.stats, d.stats_parts = st.data_ptr(), parts
                 self.stats_of[out.data_ptr()] = (st, parts)
+        else:
+            if res is not None:
+                d.res = res.data_ptr()
+            d.schedule = 1 if impl == 0 else d.schedule
+            if impl == 0 and not out_nchw and self.split_k:
+                splits = splits if splits > 1 else self._splits_for(B, Hm, Wm, cout, len(phases), nkb_min, bool(w_batch_stride))
+                if splits > 1:
+                    need = len(phases) * splits * B * Hm * Wm * cout
+                    if self.ws is None or self.ws.numel() < need:
+                        self.ws = self._new((need,), torch.float32)
+                    d.splits, d.ws, d.ws_elems = splits, self.ws.data_ptr(), self.ws.numel()
+                    launches = 2
         self.descs.append(d)
         self._op(self.L.its_conv_igemm, C.byref(d), impl, flops=flops, launches=launches,
                  kind="tapgemm_sm100" if impl == 0 else "tapgemm_cudacore")
@@ -383,6 +448,7 @@ class UNetPlan:
         self.gn_partials = None
         self.ws, self.split_k = None, True
         self.stats_of, self.schedule, self.fold_residual = {}, 0, True
+        self.ws_persist, self.sm_count = None, 148
         self.x_in = self._new((self.n_img_in, 3, H, W), torch.float32)
         self.t_dev = torch.zeros(1, dtype=torch.int32, device=self.dev)
         self.t_idx = torch.zeros(B, dtype=torch.int64, device=self.dev)

@@ -17,7 +17,7 @@ dev = torch.device("cuda:0")
 SHAPES = [  # H, Cin, Cout, k
     (32, 128, 128, 3), (32, 256, 128, 3), (32, 384, 128, 3),
     (16, 256, 256, 3), (16, 512, 256, 3), (16, 256, 256, 1), (16, 256, 512, 1),
-    (8, 384, 384, 3), (8, 768, 384, 3),
+    (8, 384, 384, 3), (8, 768, 384, 3), (8, 256, 256, 3),
     (4, 512, 512, 3), (4, 1024, 512, 3),
 ]
 print(f"schedule={schedule} bn={bn} B={B} cluster={cluster}")
@@ -26,11 +26,10 @@ for H, Cin, Cout, k in SHAPES:
     w = pack_conv_weight(torch.randn(Cout, Cin, k, k, device=dev) / 30).to(torch.bfloat16).contiguous()
     bias = torch.randn(Cout, device=dev)
     plan = UNetPlan.scratch(dev, B, 0)
-    plan.split_k = schedule != 2
     plan.schedule = schedule
     plan.conv([(x, Cin, 0, 1, False)], [(taps_square(k), 0, 0, 0)], H, H, w, Cout, bias=bias)
     d = plan.descs[0]
-    if bn and Cout % bn == 0:
+    if bn and Cout % bn == 0 and d.splits <= 1:
         d.bn = bn
     d.cluster = cluster
     for _ in range(3):
@@ -47,4 +46,4 @@ for H, Cin, Cout, k in SHAPES:
     torch.cuda.synchronize()
     us = e0.elapsed_time(e1) * 1e3 / 20
     flops = 2 * B * H * H * Cout * Cin * k * k
-    print(f"H={H:2d} Cin={Cin:4d} Cout={Cout:3d} k={k} splits={d.splits} stats={'y' if d.stats else 'n'}: {us:7.1f} us  {flops/us/1e6:7.1f} TFLOP/s")
+    print(f"H={H:2d} Cin={Cin:4d} Cout={Cout:3d} k={k} bn={d.bn} splits={d.splits} stats={'y' if d.stats else 'n'}: {us:7.1f} us  {flops/us/1e6:7.1f} TFLOP/s")

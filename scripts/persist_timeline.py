@@ -15,15 +15,18 @@ Cin = int(sys.argv[2]) if len(sys.argv) > 2 else 128
 Cout = int(sys.argv[3]) if len(sys.argv) > 3 else 128
 B = int(sys.argv[4]) if len(sys.argv) > 4 else 64
 bn = int(sys.argv[5]) if len(sys.argv) > 5 else 0
+split = int(sys.argv[6]) if len(sys.argv) > 6 else 0
 dev = torch.device("cuda:0")
 x = torch.randn(B, H, H, Cin, device=dev).to(torch.bfloat16)
 w = pack_conv_weight(torch.randn(Cout, Cin, 3, 3, device=dev) / 30).to(torch.bfloat16).contiguous()
 bias = torch.randn(Cout, device=dev)
 plan = UNetPlan.scratch(dev, B, 0)
-plan.split_k, plan.schedule = False, 2
+plan.split_k, plan.schedule = bool(split), 2
 out = plan.conv([(x, Cin, 0, 1, False)], [(taps_square(3), 0, 0, 0)], H, H, w, Cout, bias=bias)
 d = plan.descs[0]
-d.bn = bn
+if bn:
+    d.bn = bn
+print('bn', d.bn, 'splits', d.splits)
 dbg = torch.zeros(256, 64, dtype=torch.int64, device=dev)
 for _ in range(3):
     plan.run()
@@ -40,7 +43,7 @@ g0 = t[:, 0].min()
 ntile = int((t[0, 8:16] != 0).sum())
 print("cta sm start_us setup_us | per tile: acc_complete_us / epilogue_done_us ... | end_us")
 order = np.argsort(t[:, 0])
-for i in list(order[:4]) + list(order[-3:]):
+for i in list(order[:4]) + list(order[len(order)//2:len(order)//2+2]) + list(order[-4:]):
     r = t[i]
     c0 = r[1]
     us = lambda v: (v - c0) / clk / 1e3
