@@ -248,6 +248,15 @@ int its_softmax_rows(void* probs_bf16, const float* scores, int64_t n_rows,
 int its_attention_small(void* out, const void* qkv, int32_t n_img, int32_t N,
                         int32_t C, float scale, void* stream);
 
+/* Fused attention core for N = 256 tokens (the 16x16 maps of Model.py:153-158):
+ * out[b] = softmax(scale * Q[b] K[b]^T) V[b] + bias_v, with the scores in TMEM and
+ * the probabilities in shared memory only.  qk is NHWC bf16 [n_img][N][2C] (q|k),
+ * vT is bf16 [n_img][C][N] (V transposed, as the V projection with the weights as
+ * the A operand writes it), out is [n_img][N][C].  C a multiple of 64, <= 384. */
+int its_attention_fused(void* out, const void* qk, const void* vT,
+                        const float* bias_v, int32_t n_img, int32_t N, int32_t C,
+                        float scale, void* stream);
+
 /* ------------------------------------------------------------------------
  * Verifiers and selection.
  *   its_image_stats: per image mean, unbiased variance, min and the L2-

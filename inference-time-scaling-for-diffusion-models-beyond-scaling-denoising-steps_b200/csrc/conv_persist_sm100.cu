@@ -173,6 +173,7 @@ tapgemm_persist_kernel(const __grid_constant__ TapGemmParams p, const __grid_con
       const TileCoord c = decode_tile(p, wi.tile, tiles_m, tiles_n, BN, MT);
       const DevPhase& ph = p.phase[c.phase];
       const int kb0 = (ph.nkb * wi.split) / S, kb1 = (ph.nkb * (wi.split + 1)) / S;
+      const int wb = (p.w_batch_stride != 0) ? c.tb * p.bb : 0;   // per-image B operand (attention)
       int g = 0;
       for (int t = 0; t < ph.ntaps && g < kb1; ++t) {
         const int si = ph.src[t];
@@ -192,7 +193,7 @@ tapgemm_persist_kernel(const __grid_constant__ TapGemmParams p, const __grid_con
             uint8_t* a_dst = smem + stage * L::STAGE_BYTES;
             mbar_expect_tx(&full_bar[stage], (uint32_t)L::STAGE_BYTES);
             tma_load_4d(a_dst, tm, &full_bar[stage], cb * BK, cx, cy, cb_img);
-            tma_load_3d(a_dst + MT * A_BYTES, &tmB, &full_bar[stage], ph.w_k0 + g * BK, c.n0, 0);
+            tma_load_3d(a_dst + MT * A_BYTES, &tmB, &full_bar[stage], ph.w_k0 + g * BK, c.n0, wb);
           }
           __syncwarp();
           ++it;
@@ -505,14 +506,13 @@ static int persist_bn(const its_conv_desc* d, const TapGemmParams& p) {
 }
 
 bool tapgemm_persist_eligible(const its_conv_desc* d, const TapGemmParams& p) {
-  if (p.out_fp32 || p.out_nchw || p.w_batch_stride != 0 || p.res != nullptr) return false;
+  if (p.out_fp32 || p.out_nchw || p.res != nullptr) return false;
+  if (p.w_batch_stride != 0 && (p.bb != 1 || p.splits > 1)) return false;
   if (p.Cout % 64 != 0 || p.out_c_pitch % 8 != 0) return false;
   const int bn = persist_bn(d, p);
   if (!(bn == 64 || bn == 128 || bn == 192 || bn == 256) || p.Cout % bn != 0) return false;
   if (p.bw * p.bh * p.bb != BM || p.Wm % p.bw != 0 || p.Hm % p.bh != 0) return false;
   if (p.bb > 1 && p.bh != p.Hm) return false;
-  for (int s = 0; s < p.nsrc; ++s)
-    if (p.src[s].bcast) return false;
   return true;
 }
 

@@ -81,7 +81,7 @@ class UNetPlan:
         self.gn_partials, self.tproj, self.cproj = None, None, None
         self.ws, self.split_k = None, True
         self.stats_of, self.schedule, self.fold_residual = {}, 0, True
-        self.ws_persist, self.sm_count = None, 148
+        self.ws_persist, self.sm_count, self.fused_attention = None, 148, True
         return self
 
     # ------------------------------------------------------------ buffers --
@@ -367,7 +367,16 @@ class UNetPlan:
             # V^T[b] = Wv . a[b]^T : weights are the A operand, the image is the B operand
             wv_img = self._hold(wv.reshape(1, 1, Cc, Cc), BF16)
             vT = self.conv([(wv_img, Cc, 0, 1, True)], [(one, 0, 0, 0)], 1, Cc, a.view(B, N, Cc), N,
-                           w_batch_stride=N * Cc, out_shape=(B, 1, Cc, N))
+                           w_batch_stride=N * Cc, out_shape=(B, 1, Cc, N), want_stats=False)
+            if N == 256 and Cc % 64 == 0 and Cc <= 384 and self._impl_for([Cc], Cc) == 0 and self.fused_attention:
+                # scores in TMEM, probabilities in shared memory: one launch for QK^T, softmax and PV
+                o = self._new((B, H, W, Cc))
+                bvh = self._hold(bv, torch.float32)
+                self._op(self.L.its_attention_fused, o.data_ptr(), qk.data_ptr(), vT.data_ptr(), bvh.data_ptr(), B, N,
+                         Cc, scale, flops=4 * B * N * N * Cc, kind="attention_fused")
+                wp = self._hold(at.proj.weight.detach().float()[:, :, 0, 0], BF16)
+                bp = self._hold(at.proj.bias, torch.float32)
+                return self.conv([(o, Cc, 0, 1, False)], [(one, 0, 0, 0)], H, W, wp, Cc, bias=bp, res=x)
             # S = scale * Q K^T (fp32), per image
             k_view = qk.view(B, N, 2 * Cc)[:, :, Cc:]
             S = self.conv([(qk, Cc, 0, 1, False)], [(one, 0, 0, 0)], H, W, k_view, N, alpha=scale,
@@ -448,7 +457,7 @@ class UNetPlan:
         self.gn_partials = None
         self.ws, self.split_k = None, True
         self.stats_of, self.schedule, self.fold_residual = {}, 0, True
-        self.ws_persist, self.sm_count = None, 148
+        self.ws_persist, self.sm_count, self.fused_attention = None, 148, True
         self.x_in = self._new((self.n_img_in, 3, H, W), torch.float32)
         self.t_dev = torch.zeros(1, dtype=torch.int32, device=self.dev)
         self.t_idx = torch.zeros(B, dtype=torch.int64, device=self.dev)
