@@ -119,6 +119,7 @@ int its_linear(float* y, const float* x, const float* W, const float* bias,
  * they are reduced, in a fixed order and in double precision, from the partial
  * sums the producing tap-GEMM wrote (its_conv_desc.stats), and the launch is one
  * streaming normalise+Swish pass (its_group_norm_apply).
+ * out_fp16 != 0 stores IEEE fp16 (inputs are always bf16 feature maps).
  * Deterministic (no float atomics).  chunks <= 8: ONE launch, the chunks of an
  * image form a thread-block cluster and exchange partial sums through distributed
  * shared memory; chunks > 8: two launches through `partials`, scratch of
@@ -128,14 +129,14 @@ int its_group_norm(void* out, const void* src0, int32_t C0, const void* src1,
                    int32_t C1, const float* gamma, const float* beta,
                    int32_t n_img, int32_t HW, int32_t groups, float eps,
                    int32_t silu, float* partials, int32_t chunks,
-                   void* stream);
+                   int32_t out_fp16, void* stream);
 
 int its_group_norm_apply(void* out, const void* src0, int32_t C0,
                          const float* stats0, int32_t parts0, const void* src1,
                          int32_t C1, const float* stats1, int32_t parts1,
                          const float* gamma, const float* beta, int32_t n_img,
                          int32_t HW, int32_t groups, float eps, int32_t silu,
-                         void* stream);
+                         int32_t out_fp16, void* stream);
 
 /* ------------------------------------------------------------------------
  * Head / tail convolutions (CUDA-core special cases, fp32 weights).
@@ -149,6 +150,13 @@ int its_group_norm_apply(void* out, const void* src0, int32_t C0,
 int its_conv_head(void* out, const float* x, const float* W, const float* bias,
                   int32_t n_img, int32_t n_img_in, int32_t H, int32_t Wd,
                   int32_t Cin, int32_t Cout, void* stream);
+/* Head on the tensor cores: the 3x3xCin patch of every pixel as one 128-channel
+ * bf16 pixel [x_hi | x_lo | x_hi | 0] (x_hi = bf16(x), x_lo = bf16(x - x_hi)); a
+ * 1x1 its_conv_igemm against [w_hi | w_hi | w_lo | 0] then reproduces the fp32
+ * convolution of Model.py:269 to ~16 mantissa bits.  out NHWC bf16
+ * [n_img][H][W][128]; image b reads input image b % n_img_in.              */
+int its_head_patches(void* out, const float* x, int32_t n_img, int32_t n_img_in,
+                     int32_t H, int32_t Wd, int32_t Cin, void* stream);
 int its_conv_tail(float* out, const void* act, const float* W,
                   const float* bias, int32_t n_img, int32_t H, int32_t Wd,
                   int32_t Cin, int32_t Cout, void* stream);
@@ -179,6 +187,12 @@ typedef struct {
   int32_t H, W;          /* source spatial size                          */
   int32_t stride;        /* 1 or 2: source pixel = row pixel*stride+tap  */
   int32_t bcast;         /* 1: the same image for every b (batch size 1) */
+  int32_t fp16;          /* 1: this tensor AND the weight columns of its taps
+                            hold IEEE fp16 instead of bf16 (both operands of
+                            an MMA must share the format).  GroupNorm
+                            outputs are bounded, so they and their weights
+                            use fp16's 3 extra mantissa bits; raw feature
+                            maps keep bf16's range                         */
 } its_src_t;
 
 typedef struct {

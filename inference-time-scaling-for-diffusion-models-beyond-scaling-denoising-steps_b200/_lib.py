@@ -18,13 +18,14 @@ SYMBOLS = [
     "its_philox_normal", "its_step_advance", "its_time_embed", "its_embed_rows", "its_linear",
     "its_group_norm", "its_conv_head", "its_conv_tail", "its_conv_igemm", "its_softmax_rows",
     "its_attention_small", "its_image_stats", "its_candidate_scores", "its_argmax_first",
-    "its_group_norm_apply", "its_conv_stats_parts", "its_set_pdl", "its_attention_fused",
+    "its_group_norm_apply", "its_conv_stats_parts", "its_set_pdl", "its_attention_fused", "its_head_patches",
 ]
 
 
 class Src(C.Structure):
     _fields_ = [("ptr", C.c_void_p), ("c_pitch", C.c_int32), ("c_off", C.c_int32), ("C", C.c_int32),
-                ("H", C.c_int32), ("W", C.c_int32), ("stride", C.c_int32), ("bcast", C.c_int32)]
+                ("H", C.c_int32), ("W", C.c_int32), ("stride", C.c_int32), ("bcast", C.c_int32),
+                ("fp16", C.c_int32)]
 
 
 class Phase(C.Structure):
@@ -80,10 +81,11 @@ def lib() -> C.CDLL:
     L.its_time_embed.argtypes = [vp, vp, vp, vp, i32, i32, vp]
     L.its_embed_rows.argtypes = [vp, vp, vp, vp, i32, i32, i32, vp]
     L.its_linear.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]
-    L.its_group_norm.argtypes = [vp, vp, i32, vp, i32, vp, vp, i32, i32, i32, f32, i32, vp, i32, vp]
-    L.its_group_norm_apply.argtypes = [vp, vp, i32, vp, i32, vp, i32, vp, i32, vp, vp, i32, i32, i32, f32, i32, vp]
+    L.its_group_norm.argtypes = [vp, vp, i32, vp, i32, vp, vp, i32, i32, i32, f32, i32, vp, i32, i32, vp]
+    L.its_group_norm_apply.argtypes = [vp, vp, i32, vp, i32, vp, i32, vp, i32, vp, vp, i32, i32, i32, f32, i32, i32, vp]
     L.its_conv_stats_parts.argtypes = [C.POINTER(ConvDesc)]
     L.its_conv_head.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]
+    L.its_head_patches.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp]
     L.its_conv_tail.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]
     L.its_conv_igemm.argtypes = [C.POINTER(ConvDesc), i32, vp]
     L.its_softmax_rows.argtypes = [vp, vp, i64, i32, vp]

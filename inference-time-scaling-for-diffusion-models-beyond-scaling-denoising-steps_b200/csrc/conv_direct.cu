@@ -3,6 +3,7 @@
 // tap-GEMM the tcgen05 kernel computes (debug twin + channel counts that are not
 // multiples of 64).
 #include "tapgemm.cuh"
+#include <cuda_fp16.h>
 
 namespace its {
 
@@ -64,6 +65,47 @@ __global__ void __launch_bounds__(256) conv_head_kernel(
       *reinterpret_cast<bf16x8*>(orow + c0) = pack8(acc);
       *reinterpret_cast<bf16x8*>(orow + c0 + 8) = pack8(acc + 8);
     }
+  }
+}
+
+
+// ------------------------------------------------------- head patches ----
+// The Cin=3 head as a tensor-core GEMM: every output pixel's 3x3xCin input patch is written as
+// one 128-channel bf16 "pixel" [x_hi | x_lo | x_hi | 0...] (x_hi = bf16(x), x_lo = bf16(x - x_hi)),
+// to be multiplied with the packed weights [w_hi | w_hi | w_lo | 0] by a 1x1 tap-GEMM: the three
+// products x_hi*w_hi + x_lo*w_hi + x_hi*w_lo keep ~16 mantissa bits of the fp32 convolution
+// (Model.py:269 runs it in fp32; x_t reaches +-30 at early steps).
+__global__ void __launch_bounds__(256) head_patches_kernel(__nv_bfloat16* __restrict__ out,
+                                                           const float* __restrict__ x, long long nvec,
+                                                           int n_img_in, int H, int Wd, int Cin) {
+  pdl_prologue();
+  const int K = Cin * 9;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i & 15);
+    const long long pix = i >> 4;
+    const int xw = (int)(pix % Wd);
+    const int y = (int)((pix / Wd) % H);
+    const int b = (int)(pix / ((long long)Wd * H));
+    const float* xin = x + (long long)(b % n_img_in) * Cin * H * Wd;
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = v * 8 + j;
+      const int term = k / K, t = k - term * K;
+      float val = 0.f;
+      if (term < 3) {
+        const int ci = t / 9, r = t - ci * 9, ky = r / 3, kx = r - ky * 3;
+        const int yy = y + ky - 1, xx = xw + kx - 1;
+        if (yy >= 0 && yy < H && xx >= 0 && xx < Wd) {
+          const float xv = __ldg(xin + ((long long)ci * H + yy) * Wd + xx);
+          const float hi = __bfloat162float(__float2bfloat16_rn(xv));
+          val = (term == 1) ? xv - hi : hi;
+        }
+      }
+      f[j] = val;
+    }
+    *reinterpret_cast<bf16x8*>(out + i * 8) = pack8(f);
   }
 }
 
@@ -136,7 +178,9 @@ __global__ void __launch_bounds__(128) tapgemm_ref_kernel(const TapGemmParams p)
       const __nv_bfloat16* a =
           s.ptr + (((long long)(s.bcast ? 0 : b) * s.H + yy) * s.W + xx) * s.c_pitch;
       for (int c = 0; c < s.C; ++c)
-        acc = fmaf(__bfloat162float(a[c]), __bfloat162float(wrow[k + c]), acc);
+        acc = s.fp16 ? fmaf(__half2float(reinterpret_cast<const __half*>(a)[c]),
+                            __half2float(reinterpret_cast<const __half*>(wrow)[k + c]), acc)
+                     : fmaf(__bfloat162float(a[c]), __bfloat162float(wrow[k + c]), acc);
     }
     k += s.C;
   }
@@ -184,7 +228,7 @@ int tapgemm_build_params(const its_conv_desc* d, TapGemmParams* p, bool need_k64
     if (need_k64) ITS_REQUIRE(in.C % 64 == 0, "its_conv_igemm: src %d C=%d not a multiple of 64 (use impl=1)", s, in.C);
     DevSrc& o = p->src[s];
     o.ptr = static_cast<const __nv_bfloat16*>(in.ptr) + in.c_off;
-    o.c_pitch = in.c_pitch; o.C = in.C; o.H = in.H; o.W = in.W; o.stride = in.stride; o.bcast = in.bcast;
+    o.c_pitch = in.c_pitch; o.C = in.C; o.H = in.H; o.W = in.W; o.stride = in.stride; o.bcast = in.bcast; o.fp16 = in.fp16;
   }
   for (int f = 0; f < d->nphases; ++f) {
     const its_phase_t& in = d->phase[f];
@@ -261,6 +305,21 @@ extern "C" int its_conv_head(void* out, const float* x, const float* W, const fl
   ITS_LAUNCH(conv_head_kernel<3>, dim3((unsigned)blocks), dim3(256), smem, as_stream(stream), 
       static_cast<__nv_bfloat16*>(out), x, W, bias, n_img, n_img_in, H, Wd, Cout);
   ITS_CHECK_LAUNCH();
+  return ITS_OK;
+}
+
+
+extern "C" int its_head_patches(void* out, const float* x, int32_t n_img, int32_t n_img_in, int32_t H,
+                                int32_t Wd, int32_t Cin, void* stream) {
+  using namespace its;
+  ITS_REQUIRE(out && x, "its_head_patches: null pointer");
+  ITS_REQUIRE(n_img > 0 && n_img_in > 0 && H > 0 && Wd > 0 && Cin >= 1 && Cin * 27 <= 128,
+              "its_head_patches: unsupported shape Cin=%d (3 * 9 * Cin must fit 128 patch channels)", Cin);
+  const long long nvec = (long long)n_img * H * Wd * 16;
+  long long blocks = (nvec + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  ITS_LAUNCH(head_patches_kernel, dim3((unsigned)blocks), dim3(256), 0, as_stream(stream),
+             static_cast<__nv_bfloat16*>(out), x, nvec, n_img_in, H, Wd, Cin);
   return ITS_OK;
 }
 

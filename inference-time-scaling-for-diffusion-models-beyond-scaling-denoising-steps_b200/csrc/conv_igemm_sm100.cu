@@ -193,8 +193,10 @@ tapgemm_sm100_kernel(const __grid_constant__ TapGemmParams p, const __grid_const
   } else if (warp == 1) {
     // ------------------------------------------------- MMA issuer -----
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(BN);
+      int tap = 0, tap_end = 0;   // walks the taps along K: each tap's source fixes the operand format
       for (int kb = 0; kb < nkb; ++kb) {
+        while (kb0 + kb >= tap_end) tap_end += p.src[ph.src[tap++]].C / BK;
+        const uint32_t idesc = make_idesc(BN, p.src[ph.src[tap - 1]].fp16 != 0);
         const int stage = kb % STAGES;
         const uint32_t parity = (uint32_t)((kb / STAGES) & 1);
         mbar_wait(&full_bar[stage], parity);

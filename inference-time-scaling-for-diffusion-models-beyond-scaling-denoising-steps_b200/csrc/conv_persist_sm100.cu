@@ -203,12 +203,14 @@ tapgemm_persist_kernel(const __grid_constant__ TapGemmParams p, const __grid_con
   } else if (warp == 1) {
     // ------------------------------------------------- MMA issuer -----
     // the whole warp walks the loop (converged waits), one elected lane issues
-    constexpr uint32_t idesc = make_idesc(BN);
     uint32_t it = 0, j = 0;
     for (int w = blockIdx.x; w < total_items; w += gridDim.x, ++j) {
       const WorkItem wi = decode_item(w, total_tiles, S);
-      const int nkb_phase = p.phase[wi.tile / (tiles_m * tiles_n)].nkb;
-      const int nkb = (nkb_phase * (wi.split + 1)) / S - (nkb_phase * wi.split) / S;
+      const DevPhase& ph = p.phase[wi.tile / (tiles_m * tiles_n)];
+      const int nkb_phase = ph.nkb;
+      const int kb0 = (nkb_phase * wi.split) / S;
+      const int nkb = (nkb_phase * (wi.split + 1)) / S - kb0;
+      int tap = 0, tap_end = 0;   // walks the taps along K: each tap's source fixes the operand format
       const uint32_t buf = j & 1u;
       mbar_wait(&tempty_bar[buf], ((j >> 1) & 1u) ^ 1u);   // epilogue has drained this buffer
       tcgen05_fence_after();
@@ -216,6 +218,8 @@ tapgemm_persist_kernel(const __grid_constant__ TapGemmParams p, const __grid_con
       for (int kb = 0; kb < nkb; ++kb, ++it) {
         const uint32_t stage = it % STAGES;
         const uint32_t parity = (it / STAGES) & 1u;
+        while (kb0 + kb >= tap_end) tap_end += p.src[ph.src[tap++]].C / BK;
+        const uint32_t idesc = make_idesc(BN, p.src[ph.src[tap - 1]].fp16 != 0);
         mbar_wait(&full_bar[stage], parity);
         tcgen05_fence_after();
         if (elect_one_sync()) {

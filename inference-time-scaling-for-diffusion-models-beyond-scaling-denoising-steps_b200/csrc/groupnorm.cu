@@ -21,7 +21,7 @@ struct GnArgs {
   const float* gamma;
   const float* beta;
   float* partials;
-  int C0, C1, C, HW, groups, chunks, silu;
+  int C0, C1, C, HW, groups, chunks, silu, out_fp16;
   float eps;
 };
 
@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const GnArgs a) {
       float v = fmaf(f[i], scale[i], shift[i]);
       f[i] = a.silu ? silu_f(v) : v;
     }
-    *reinterpret_cast<bf16x8*>(a.out + pix * a.C + cv * 8) = pack8(f);
+    *reinterpret_cast<bf16x8*>(a.out + pix * a.C + cv * 8) = a.out_fp16 ? pack8_half(f) : pack8(f);
   }
 }
 
@@ -236,7 +236,7 @@ __global__ void __launch_bounds__(GN_THREADS) gn_cluster_kernel(const GnArgs a) 
       const float v = fmaf(f[i], scale[i], shift[i]);
       f[i] = a.silu ? silu_f(v) : v;
     }
-    *reinterpret_cast<bf16x8*>(a.out + pix * a.C + cv * 8) = pack8(f);
+    *reinterpret_cast<bf16x8*>(a.out + pix * a.C + cv * 8) = a.out_fp16 ? pack8_half(f) : pack8(f);
   }
 }
 
@@ -255,7 +255,7 @@ struct GnStatArgs {
   const float* beta;
   const float2* st0;
   const float2* st1;
-  int C0, C1, C, HW, groups, parts0, parts1, silu, chunks;
+  int C0, C1, C, HW, groups, parts0, parts1, silu, chunks, out_fp16;
   float eps;
 };
 
@@ -352,7 +352,7 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_stats_kernel(const GnStat
           const float v = fmaf(f[i], scale[i], shift[i]);
           f[i] = a.silu ? silu_fast(v) : v;
         }
-        *reinterpret_cast<bf16x8*>(a.out + ((long long)img * a.HW + p) * a.C + cv * 8) = pack8(f);
+        *reinterpret_cast<bf16x8*>(a.out + ((long long)img * a.HW + p) * a.C + cv * 8) = a.out_fp16 ? pack8_half(f) : pack8(f);
       }
     }
   }
@@ -389,7 +389,7 @@ static int launch_gn_cluster(const GnArgs& a, int n_img, size_t dyn_bytes, cudaS
 extern "C" int its_group_norm(void* out, const void* src0, int32_t C0, const void* src1, int32_t C1,
                               const float* gamma, const float* beta, int32_t n_img, int32_t HW,
                               int32_t groups, float eps, int32_t silu, float* partials,
-                              int32_t chunks, void* stream) {
+                              int32_t chunks, int32_t out_fp16, void* stream) {
   using namespace its;
   ITS_REQUIRE(out && src0 && gamma && beta && partials, "its_group_norm: null pointer");
   ITS_REQUIRE(C1 == 0 || src1 != nullptr, "its_group_norm: C1 > 0 needs src1");
@@ -404,6 +404,7 @@ extern "C" int its_group_norm(void* out, const void* src0, int32_t C0, const voi
   a.out = static_cast<__nv_bfloat16*>(out);
   a.gamma = gamma; a.beta = beta; a.partials = partials;
   a.C0 = C0; a.C1 = C1; a.C = C; a.HW = HW; a.groups = groups; a.chunks = chunks; a.silu = silu;
+  a.out_fp16 = out_fp16;
   a.eps = eps;
   if (chunks <= 8) {
     // one launch: cluster of `chunks` CTAs per image
@@ -423,7 +424,8 @@ extern "C" int its_group_norm(void* out, const void* src0, int32_t C0, const voi
 extern "C" int its_group_norm_apply(void* out, const void* src0, int32_t C0, const float* stats0,
                                     int32_t parts0, const void* src1, int32_t C1, const float* stats1,
                                     int32_t parts1, const float* gamma, const float* beta, int32_t n_img,
-                                    int32_t HW, int32_t groups, float eps, int32_t silu, void* stream) {
+                                    int32_t HW, int32_t groups, float eps, int32_t silu, int32_t out_fp16,
+                                    void* stream) {
   using namespace its;
   ITS_REQUIRE(out && src0 && stats0 && gamma && beta, "its_group_norm_apply: null pointer");
   ITS_REQUIRE(C1 == 0 || (src1 != nullptr && stats1 != nullptr), "its_group_norm_apply: C1 > 0 needs src1 and stats1");
@@ -441,7 +443,7 @@ extern "C" int its_group_norm_apply(void* out, const void* src0, int32_t C0, con
   a.st0 = reinterpret_cast<const float2*>(stats0);
   a.st1 = reinterpret_cast<const float2*>(stats1);
   a.C0 = C0; a.C1 = C1; a.C = C; a.HW = HW; a.groups = groups; a.parts0 = parts0; a.parts1 = parts1;
-  a.silu = silu; a.eps = eps;
+  a.silu = silu; a.eps = eps; a.out_fp16 = out_fp16;
   // ~32 KB of activations per CTA keeps >= 2 waves on 148 SMs for the large maps
   long long chunks = ((long long)HW * C * 2 + 32767) / 32768;
   if (chunks < 1) chunks = 1;

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
@@ -87,6 +88,17 @@ __device__ __forceinline__ bf16x8 pack8(const float* f) {
   bf16x8 p;
 #pragma unroll
   for (int i = 0; i < 4; ++i) p.v[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  return p;
+}
+
+// 8 floats -> 8 IEEE halves in the same 16-byte container (GroupNorm outputs, see its_src_t.fp16)
+__device__ __forceinline__ bf16x8 pack8_half(const float* f) {
+  bf16x8 p;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __half2 h = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+    p.v[i] = *reinterpret_cast<const __nv_bfloat162*>(&h);
+  }
   return p;
 }
 

@@ -132,9 +132,11 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
   d |= (uint64_t)2 << 61;                        // layout type: SWIZZLE_128B
   return d;
 }
-// Instruction descriptor: D fp32, A/B bf16, both K-major, M=128, N=BN.
-__host__ __device__ constexpr uint32_t make_idesc(int bn) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+// Instruction descriptor: D fp32, A and B both bf16 (format 1) or both IEEE fp16 (format 0; mixed
+// formats are an illegal instruction), both K-major, M=128, N=BN.
+__host__ __device__ constexpr uint32_t make_idesc(int bn, bool fp16 = false) {
+  return (1u << 4) | (fp16 ? 0u : ((1u << 7) | (1u << 10))) | ((uint32_t)(bn >> 3) << 17) |
+         ((uint32_t)(BM >> 4) << 24);
 }
 
 __host__ __device__ constexpr int tmem_cols_for(int bn) { return bn <= 32 ? 32 : bn <= 64 ? 64 : bn <= 128 ? 128 : 256; }

@@ -8,7 +8,7 @@ namespace its {
 
 struct DevSrc {
   const __nv_bfloat16* ptr;  // already offset by c_off
-  int c_pitch, C, H, W, stride, bcast;
+  int c_pitch, C, H, W, stride, bcast, fp16;
 };
 
 struct DevPhase {

@@ -25,6 +25,14 @@ from . import _lib
 from ._lib import ConvDesc
 
 BF16 = torch.bfloat16
+FP16 = torch.float16
+# Operand formats.  Both operands of an MMA share one 16-bit format.  GroupNorm(+Swish) outputs are
+# bounded, so they are stored as IEEE fp16 and the weight columns multiplying them are packed as
+# fp16 too (3 more mantissa bits than bf16: weight rounding was the largest single error term of
+# the bf16 path); raw feature maps (residual stream, skips, q/k/v) keep bf16's range, and so do the
+# weight columns of the taps that read them.  ITS_FP16_GN=0 restores all-bf16 (triage).
+import os as _os
+FP16_GN = _os.environ.get("ITS_FP16_GN", "1") != "0"
 
 
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
@@ -82,6 +90,8 @@ class UNetPlan:
         self.ws, self.split_k = None, True
         self.stats_of, self.schedule, self.fold_residual = {}, 0, True
         self.ws_persist, self.sm_count, self.fused_attention = None, 148, True
+        self.head_on_tensor_cores = True
+        self.gn_dtype = FP16 if (FP16_GN and impl != 1) else BF16
         return self
 
     # ------------------------------------------------------------ buffers --
@@ -189,6 +199,7 @@ class UNetPlan:
             s = d.src[i]
             s.ptr, s.c_pitch, s.c_off, s.C = t.data_ptr(), t.shape[-1], c_off, c_used
             s.H, s.W, s.stride, s.bcast = t.shape[1], t.shape[2], stride, int(bcast)
+            s.fp16 = int(t.dtype == FP16)
         d.nphases = len(phases)
         flops = 0
         for i, (taps, w_k0, py, px) in enumerate(phases):
@@ -219,7 +230,7 @@ class UNetPlan:
         can_fold = (res is not None and impl == 0 and self.fold_residual and self.schedule != 1
                     and len(phases) == 1 and alpha == 1.0 and not out_fp32 and not out_nchw and not w_batch_stride
                     and len(srcs) < _lib.MAX_SRC and cout % 64 == 0 and res.shape[-1] == cout
-                    and (w_pitch or w.shape[-1]) == w.shape[-1] and w.dim() == 2)
+                    and (w_pitch or w.shape[-1]) == w.shape[-1] and w.dim() == 2 and w.dtype == torch.float32)
         if can_fold:
             d.res = None
         persistent = impl == 0 and self.L.its_conv_stats_parts(C.byref(d)) > 0
@@ -233,16 +244,17 @@ class UNetPlan:
                 # identity shortcut as one more K block with identity weights (exact: 1.0 * bf16 value
                 # in the fp32 accumulator): the persistent schedule has no residual read in its epilogue
                 k_used = sum(srcs[si][1] for si, _, _ in phases[0][0])
-                w = self._hold(torch.cat([w[:, :k_used].float(), torch.eye(cout, device=w.device)], 1), BF16)
+                w = torch.cat([w[:, :k_used].float(), torch.eye(cout, device=w.device)], 1)
                 i = d.nsrc
                 sN = d.src[i]
                 sN.ptr, sN.c_pitch, sN.c_off, sN.C = res.data_ptr(), res.shape[-1], 0, cout
                 sN.H, sN.W, sN.stride, sN.bcast = res.shape[1], res.shape[2], 1, 0
+                sN.fp16 = int(res.dtype == FP16)
                 d.nsrc = i + 1
                 ph = d.phase[0]
                 ph.src[ph.ntaps], ph.dy[ph.ntaps], ph.dx[ph.ntaps] = i, 0, 0
                 ph.ntaps += 1
-                d.w, d.w_pitch = w.data_ptr(), w.shape[-1]
+                d.w_pitch = w.shape[-1]
             d.bn = bn
             if splits > 1:
                 tiles = self._tiles_at(B, Hm, Wm) * (cout // bn) * len(phases)
@@ -270,6 +282,21 @@ class UNetPlan:
                         self.ws = self._new((need,), torch.float32)
                     d.splits, d.ws, d.ws_elems = splits, self.ws.data_ptr(), self.ws.numel()
                     launches = 2
+        if w.dtype == torch.float32:
+            # real weights: pack every tap's columns in the 16-bit format of the source it multiplies
+            w16 = torch.empty(w.shape, dtype=torch.int16, device=self.dev)
+            wf = w.to(self.dev)
+            for f in range(d.nphases):
+                k = d.phase[f].w_k0
+                for t in range(d.phase[f].ntaps):
+                    sc = d.src[d.phase[f].src[t]]
+                    fmt = FP16 if sc.fp16 else BF16
+                    w16[..., k:k + sc.C] = wf[..., k:k + sc.C].to(fmt).view(torch.int16)
+                    k += sc.C
+            self.keep.append(w16)
+            d.w = w16.data_ptr()
+        elif persistent and can_fold:
+            raise RuntimeError("residual folding needs fp32 weights")
         self.descs.append(d)
         self._op(self.L.its_conv_igemm, C.byref(d), impl, flops=flops, launches=launches,
                  kind="tapgemm_sm100" if impl == 0 else "tapgemm_cudacore")
@@ -281,7 +308,8 @@ class UNetPlan:
         B, H, W, C0 = x0.shape
         C1 = x1.shape[-1] if x1 is not None else 0
         Ct = C0 + C1
-        out = self._new((B, H, W, Ct))
+        out = self._new((B, H, W, Ct), self.gn_dtype)
+        f16 = int(self.gn_dtype == FP16)
         HW = H * W
         st = [self.stats_of.get(t.data_ptr()) for t in srcs]
         if all(x is not None for x in st) and (Ct // gn.num_groups) % 4 == 0:
@@ -291,7 +319,7 @@ class UNetPlan:
             s1, p1 = st[1] if x1 is not None else (None, 0)
             self._op(self.L.its_group_norm_apply, out.data_ptr(), x0.data_ptr(), C0, s0.data_ptr(), p0, _ptr(x1), C1,
                      _ptr(s1), p1, gamma.data_ptr(), beta.data_ptr(), B, HW, gn.num_groups, float(gn.eps),
-                     int(silu), launches=1, kind="group_norm_apply")
+                     int(silu), f16, launches=1, kind="group_norm_apply")
             self.gn_bytes = getattr(self, "gn_bytes", 0) + B * HW * Ct * 2 * 2
             return out
         prow = max(1, 256 // (Ct // 8))
@@ -305,7 +333,7 @@ class UNetPlan:
         gamma, beta = self._hold(gn.weight, torch.float32), self._hold(gn.bias, torch.float32)
         self._op(self.L.its_group_norm, out.data_ptr(), x0.data_ptr(), C0, _ptr(x1), C1, gamma.data_ptr(),
                  beta.data_ptr(), B, HW, gn.num_groups, float(gn.eps), int(silu),
-                 self.gn_partials.data_ptr(), chunks, launches=1, kind="group_norm")
+                 self.gn_partials.data_ptr(), chunks, f16, launches=1, kind="group_norm")
         self.gn_bytes = getattr(self, "gn_bytes", 0) + B * HW * Ct * 2 * 2   # one read + one write, bf16
         return out
 
@@ -324,7 +352,7 @@ class UNetPlan:
         cin = sum(t.shape[-1] for t in xs)
         cout = rb.block1[2].out_channels
         a1 = self.group_norm(xs, rb.block1[0], silu=True)
-        w1 = self._hold(pack_conv_weight(rb.block1[2].weight), BF16)
+        w1 = self._hold(pack_conv_weight(rb.block1[2].weight), torch.float32)
         b1 = self._hold(rb.block1[2].bias, torch.float32)
         h1 = self.conv([(a1, cin, 0, 1, False)], [(taps_square(3), 0, 0, 0)], H, W, w1, cout, bias=b1,
                        vec=self.tproj, vec_off=proj_off, vec2=self.cproj, vec2_off=proj_off)
@@ -335,7 +363,7 @@ class UNetPlan:
         has_sc = not isinstance(rb.shortcut, torch.nn.Identity)
         if has_sc:
             ws = rb.shortcut.weight.detach().float()[:, :, 0, 0]
-            w2 = self._hold(torch.cat([w2, ws], dim=1), BF16)
+            w2 = self._hold(torch.cat([w2, ws], dim=1), torch.float32)
             b2 = self._hold(b2 + rb.shortcut.bias.detach().float(), torch.float32)
             srcs = [(a2, cout, 0, 1, False)] + [(t, t.shape[-1], 0, 1, False) for t in xs]
             taps = taps_square(3) + [(1 + i, 0, 0) for i in range(len(xs))]
@@ -343,7 +371,7 @@ class UNetPlan:
         else:
             if len(xs) != 1:
                 raise RuntimeError("identity shortcut over a concatenated input is not supported")
-            w2 = self._hold(w2, BF16)
+            w2 = self._hold(w2, torch.float32)
             b2 = self._hold(b2, torch.float32)
             h2 = self.conv([(a2, cout, 0, 1, False)], [(taps_square(3), 0, 0, 0)], H, W, w2, cout, bias=b2,
                            res=xs[0])
@@ -361,11 +389,11 @@ class UNetPlan:
         one = [(0, 0, 0)]
         tensor_path = N > 64      # batched-GEMM formulation (tcgen05, or its CUDA-core twin when forced)
         if tensor_path:
-            wqk = self._hold(torch.cat([wq, wk], 0), BF16)
+            wqk = self._hold(torch.cat([wq, wk], 0), torch.float32)
             bqk = self._hold(torch.cat([bq, bk], 0), torch.float32)
             qk = self.conv([(a, Cc, 0, 1, False)], [(one, 0, 0, 0)], H, W, wqk, 2 * Cc, bias=bqk, want_stats=False)
             # V^T[b] = Wv . a[b]^T : weights are the A operand, the image is the B operand
-            wv_img = self._hold(wv.reshape(1, 1, Cc, Cc), BF16)
+            wv_img = self._hold(wv.reshape(1, 1, Cc, Cc), a.dtype)
             vT = self.conv([(wv_img, Cc, 0, 1, True)], [(one, 0, 0, 0)], 1, Cc, a.view(B, N, Cc), N,
                            w_batch_stride=N * Cc, out_shape=(B, 1, Cc, N), want_stats=False)
             if N == 256 and Cc % 64 == 0 and Cc <= 384 and self._impl_for([Cc], Cc) == 0 and self.fused_attention:
@@ -374,7 +402,7 @@ class UNetPlan:
                 bvh = self._hold(bv, torch.float32)
                 self._op(self.L.its_attention_fused, o.data_ptr(), qk.data_ptr(), vT.data_ptr(), bvh.data_ptr(), B, N,
                          Cc, scale, flops=4 * B * N * N * Cc, kind="attention_fused")
-                wp = self._hold(at.proj.weight.detach().float()[:, :, 0, 0], BF16)
+                wp = self._hold(at.proj.weight.detach().float()[:, :, 0, 0], torch.float32)
                 bp = self._hold(at.proj.bias, torch.float32)
                 return self.conv([(o, Cc, 0, 1, False)], [(one, 0, 0, 0)], H, W, wp, Cc, bias=bp, res=x)
             # S = scale * Q K^T (fp32), per image
@@ -387,24 +415,24 @@ class UNetPlan:
             o = self.conv([(P, N, 0, 1, False)], [(one, 0, 0, 0)], H, W, vT.view(B, Cc, N), Cc, bias=bvh,
                           w_batch_stride=Cc * N, want_stats=False)
         else:
-            wqkv = self._hold(torch.cat([wq, wk, wv], 0), BF16)
+            wqkv = self._hold(torch.cat([wq, wk, wv], 0), torch.float32)
             bqkv = self._hold(torch.cat([bq, bk, bv], 0), torch.float32)
             qkv = self.conv([(a, Cc, 0, 1, False)], [(one, 0, 0, 0)], H, W, wqkv, 3 * Cc, bias=bqkv, want_stats=False)
             o = self._new((B, H, W, Cc))
             self._op(self.L.its_attention_small, o.data_ptr(), qkv.data_ptr(), B, N, Cc, scale,
                      flops=4 * B * N * N * Cc, kind="attention_small")
-        wp = self._hold(at.proj.weight.detach().float()[:, :, 0, 0], BF16)
+        wp = self._hold(at.proj.weight.detach().float()[:, :, 0, 0], torch.float32)
         bp = self._hold(at.proj.bias, torch.float32)
         return self.conv([(o, Cc, 0, 1, False)], [(one, 0, 0, 0)], H, W, wp, Cc, bias=bp, res=x)
 
     def _down(self, ds, x: torch.Tensor) -> torch.Tensor:
         B, H, W, Cc = x.shape
         if hasattr(ds, "main"):       # Model.py:96-108
-            w = self._hold(pack_conv_weight(ds.main.weight), BF16)
+            w = self._hold(pack_conv_weight(ds.main.weight), torch.float32)
             b = self._hold(ds.main.bias, torch.float32)
             taps = taps_square(3)
         else:                          # ModelCondition.py:65-73: 3x3 s2 + 5x5 s2, one accumulator
-            w = self._hold(torch.cat([pack_conv_weight(ds.c1.weight), pack_conv_weight(ds.c2.weight)], 1), BF16)
+            w = self._hold(torch.cat([pack_conv_weight(ds.c1.weight), pack_conv_weight(ds.c2.weight)], 1), torch.float32)
             b = self._hold(ds.c1.bias.detach().float() + ds.c2.bias.detach().float(), torch.float32)
             taps = taps_square(3) + taps_square(5)
         return self.conv([(x, Cc, 0, 2, False)], [(taps, 0, 0, 0)], H // 2, W // 2, w, Cc, bias=b)
@@ -425,7 +453,7 @@ class UNetPlan:
                             taps.append((0, dy, dx))
                     phases.append((taps, k0, py, px))
                     k0 += len(taps) * Cc
-            wp = self._hold(torch.cat(mats, 1), BF16)
+            wp = self._hold(torch.cat(mats, 1), torch.float32)
             b = self._hold(us.main.bias, torch.float32)
             return self.conv([(x, Cc, 0, 1, False)], phases, H, W, wp, Cc, out_scale=2, bias=b)
         # ConvTranspose2d(5, 2, 2, 1) as four phases (ModelCondition.py:80), then 3x3
@@ -442,12 +470,38 @@ class UNetPlan:
                         taps.append((0, (py + 2 - ky) // 2, (px + 2 - kx) // 2))
                 phases.append((taps, k0, py, px))
                 k0 += len(taps) * Cc
-        wp = self._hold(torch.cat(mats, 1), BF16)
+        wp = self._hold(torch.cat(mats, 1), torch.float32)
         bt = self._hold(us.t.bias, torch.float32)
         y = self.conv([(x, Cc, 0, 1, False)], phases, H, W, wp, Cc, out_scale=2, bias=bt)
-        wc = self._hold(pack_conv_weight(us.c.weight), BF16)
+        wc = self._hold(pack_conv_weight(us.c.weight), torch.float32)
         bc = self._hold(us.c.bias, torch.float32)
         return self.conv([(y, Cc, 0, 1, False)], [(taps_square(3), 0, 0, 0)], 2 * H, 2 * W, wc, Cc, bias=bc)
+
+    def head_conv(self, weight, bias, x_in: torch.Tensor, B: int, H: int, W: int) -> torch.Tensor:
+        """Model.py:269: conv3x3(3 -> ch) of the NCHW fp32 sampler state into NHWC bf16."""
+        L = self.L
+        ch = weight.shape[0]
+        n_img_in = x_in.shape[0]
+        hb = self._hold(bias, torch.float32)
+        if self._impl_for([128], ch) == 0 and self.head_on_tensor_cores:
+            # patches [x_hi | x_lo | x_hi | 0] x weights [w_hi | w_hi | w_lo | 0]: fp32-grade head on
+            # the persistent tap-GEMM, which also leaves the GroupNorm statistics of h behind
+            patches = self._new((B, H, W, 128))
+            self._op(L.its_head_patches, patches.data_ptr(), x_in.data_ptr(), B, n_img_in, H, W, 3,
+                     kind="head_patches")
+            w32 = weight.detach().float().reshape(ch, 27)
+            w_hi = w32.to(BF16).float()
+            wpk = torch.zeros(ch, 128, device=w32.device)
+            wpk[:, 0:27], wpk[:, 27:54], wpk[:, 54:81] = w_hi, w_hi, w32 - w_hi
+            h = self.conv([(patches, 128, 0, 1, False)], [([(0, 0, 0)], 0, 0, 0)], H, W, self._hold(wpk, BF16), ch,
+                          bias=hb, B=B)
+            self.flops -= 2 * B * H * W * ch * (128 - 27)     # algorithmic work is the 27-tap convolution
+            return h
+        h = self._new((B, H, W, ch))
+        hw = self._hold(weight, torch.float32)
+        self._op(L.its_conv_head, h.data_ptr(), x_in.data_ptr(), hw.data_ptr(), hb.data_ptr(), B,
+                 n_img_in, H, W, 3, ch, flops=2 * B * H * W * ch * 27, kind="conv_head")
+        return h
 
     # -------------------------------------------------------------- build --
     def _build(self):
@@ -458,6 +512,13 @@ class UNetPlan:
         self.ws, self.split_k = None, True
         self.stats_of, self.schedule, self.fold_residual = {}, 0, True
         self.ws_persist, self.sm_count, self.fused_attention = None, 148, True
+        self.head_on_tensor_cores = True
+        # debugging switches (tests/parity triage): fall back to the simpler schedule of a stage
+        import os as _os
+        self.schedule = int(_os.environ.get("ITS_SCHEDULE", "0"))
+        self.fused_attention = _os.environ.get("ITS_FUSED_ATTENTION", "1") != "0"
+        self.head_on_tensor_cores = _os.environ.get("ITS_HEAD_TC", "1") != "0"
+        self.gn_dtype = FP16 if (FP16_GN and ch % 64 == 0 and self.impl_forced != 1) else BF16
         self.x_in = self._new((self.n_img_in, 3, H, W), torch.float32)
         self.t_dev = torch.zeros(1, dtype=torch.int32, device=self.dev)
         self.t_idx = torch.zeros(B, dtype=torch.int64, device=self.dev)
@@ -502,10 +563,7 @@ class UNetPlan:
             bc = self._hold(torch.cat([rb.cond_proj[1].bias.detach().float() for rb in blocks], 0), torch.float32)
             self.cproj = self.linear(cemb, wc, bc, silu_in=True)
         # ---- head
-        h = self._new((B, H, W, ch))
-        hw, hb = self._hold(m.head.weight, torch.float32), self._hold(m.head.bias, torch.float32)
-        self._op(L.its_conv_head, h.data_ptr(), self.x_in.data_ptr(), hw.data_ptr(), hb.data_ptr(), B,
-                 self.n_img_in, H, W, 3, ch, flops=2 * B * H * W * ch * 27, kind="conv_head")
+        h = self.head_conv(m.head.weight, m.head.bias, self.x_in, B, H, W)
         hs = [h]
         for layer in m.downblocks:
             h = self._res_block(layer, [h], offs[id(layer)]) if hasattr(layer, "temb_proj") else self._down(layer, h)
@@ -524,7 +582,7 @@ class UNetPlan:
         if self._impl_for([ct], 3, True) == 0:
             # 3-channel tail on the tensor cores: N tile of 32 (rows 3..31 of the weight box are
             # TMA zero fill), epilogue writes NCHW fp32 directly (coalesced over pixels)
-            tw = self._hold(pack_conv_weight(m.tail[2].weight), BF16)
+            tw = self._hold(pack_conv_weight(m.tail[2].weight), torch.float32)
             tb = self._hold(m.tail[2].bias, torch.float32)
             self.conv([(a, ct, 0, 1, False)], [(taps_square(3), 0, 0, 0)], H, W, tw, 3, bias=tb, out=self.eps,
                       out_fp32=True, out_nchw=True)

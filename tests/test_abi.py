@@ -37,7 +37,7 @@ def test_invalid_arguments_return_error_codes(built_lib):
     rc = built_lib.its_ddpm_step(None, None, None, None, 0, 1, 4, None, None, 0.0, 0, 0, None, 0, None)
     assert rc == 1
     assert b"null pointer" in built_lib.its_last_error_string()
-    rc = built_lib.its_group_norm(1, 1, 12, None, 0, 1, 1, 1, 16, 32, 1e-5, 1, 1, 1, None)
+    rc = built_lib.its_group_norm(1, 1, 12, None, 0, 1, 1, 1, 16, 32, 1e-5, 1, 1, 1, 0, None)
     assert rc == 1 and b"multiples of 8" in built_lib.its_last_error_string()
     from its_b200._lib import ConvDesc
     d = ConvDesc()

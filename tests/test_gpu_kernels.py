@@ -170,6 +170,29 @@ def test_conv_head_and_tail(cuda_dev, built_lib):
     check_close(eps, F.conv2d(bf(a), wt, bt, padding=1), 1e-5, "tail")
 
 
+
+def test_head_on_tensor_cores_keeps_fp32_grade_accuracy(cuda_dev, built_lib):
+    """Head conv (Model.py:269) as hi/lo bf16 patches x hi/lo weights on the tap-GEMM: the only
+    rounding left is the bf16 store of the result."""
+    from its_b200.engine import UNetPlan
+    g = torch.Generator().manual_seed(6)
+    B, H, ch = 6, 32, 128
+    x = torch.randn(3, 3, H, H, generator=g).to(cuda_dev) * 30      # x_t is large at early steps
+    w = torch.randn(ch, 3, 3, 3, generator=g).to(cuda_dev) * 0.2
+    b = torch.randn(ch, generator=g).to(cuda_dev) * 0.1
+    plan = UNetPlan.scratch(cuda_dev, B)
+    out = plan.head_conv(w, b, x, B, H, H)
+    assert plan.op_info[0][0] == "head_patches" and out.data_ptr() in plan.stats_of
+    plan.run()
+    torch.cuda.synchronize()
+    ref = F.conv2d(torch.cat([x, x]), w, b, padding=1)
+    got = nchw(out)
+    assert torch.equal(got, ref.to(torch.bfloat16).float()) or \
+        (got - ref).abs().max().item() <= 2.0 ** -8 * ref.abs().max().item()
+    # a bf16-only GEMM would be ~10x worse than the bf16 store rounding bound checked here
+    frac_exact = (got == ref.to(torch.bfloat16).float()).float().mean().item()
+    assert frac_exact > 0.98, frac_exact
+
 # -------------------------------------------------------------- tap-GEMM -----
 def _conv_case(dev, impl, B, H, Cin, Cout, *, k=3, stride=1, extras=False, seed=0, alpha=0.5):
     from its_b200.engine import UNetPlan, pack_conv_weight, taps_square
@@ -188,7 +211,7 @@ def _conv_case(dev, impl, B, H, Cin, Cout, *, k=3, stride=1, extras=False, seed=
         kw = dict(vec=vec, vec_off=8, vec2=vec2, res=nhwc(res), alpha=alpha)
         ref = alpha * F.conv2d(bf(x), bf(w), None, stride=stride, padding=k // 2) + bias.view(1, -1, 1, 1) \
             + vec[:, 8:].view(B, Cout, 1, 1) + vec2.view(1, Cout, 1, 1) + bf(res)
-    wp = pack_conv_weight(w).to(torch.bfloat16).contiguous()
+    wp = pack_conv_weight(w).contiguous()       # fp32: the plan packs it in the sources' 16-bit format
     xin = nhwc(x)
     out = plan.conv([(xin, Cin, 0, stride, False)], [(taps_square(k), 0, 0, 0)], Ho, Ho, wp, Cout, bias=bias, **kw)
     plan.run()
