@@ -243,6 +243,23 @@ int tapgemm_build_params(const its_conv_desc* d, TapGemmParams* p, bool need_k64
       k += d->src[in.src[t]].C;
     }
     o.nkb = k / 64;
+    // operand format along K: taps are grouped by format (GroupNorm-output taps first, raw taps
+    // after), so one switch point describes the phase
+    o.fp16_first = d->src[in.src[0]].fp16 != 0;
+    o.kb_switch = o.nkb;
+    {
+      int kk = 0, switches = 0;
+      for (int t = 0; t < in.ntaps; ++t) {
+        const int f = d->src[in.src[t]].fp16 != 0;
+        const int prev = (t == 0) ? o.fp16_first : (d->src[in.src[t - 1]].fp16 != 0);
+        if (f != prev) {
+          ++switches;
+          o.kb_switch = kk / 64;
+        }
+        kk += d->src[in.src[t]].C;
+      }
+      ITS_REQUIRE(switches <= 1, "its_conv_igemm: phase %d interleaves fp16 and bf16 taps (group them)", f);
+    }
     ITS_REQUIRE(in.w_k0 >= 0 && in.w_k0 + k <= d->w_pitch, "its_conv_igemm: phase %d K range [%d,%d) exceeds w_pitch=%d", f, in.w_k0, in.w_k0 + k, d->w_pitch);
     if (need_k64) ITS_REQUIRE(in.w_k0 % 8 == 0, "its_conv_igemm: phase %d w_k0 alignment", f);
   }

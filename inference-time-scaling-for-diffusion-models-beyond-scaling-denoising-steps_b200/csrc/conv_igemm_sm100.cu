@@ -193,10 +193,10 @@ tapgemm_sm100_kernel(const __grid_constant__ TapGemmParams p, const __grid_const
   } else if (warp == 1) {
     // ------------------------------------------------- MMA issuer -----
     if (lane == 0) {
-      int tap = 0, tap_end = 0;   // walks the taps along K: each tap's source fixes the operand format
+      const uint32_t idesc_a = make_idesc(BN, ph.fp16_first != 0), idesc_b = make_idesc(BN, ph.fp16_first == 0);
+      const int ksw = ph.kb_switch - kb0;
       for (int kb = 0; kb < nkb; ++kb) {
-        while (kb0 + kb >= tap_end) tap_end += p.src[ph.src[tap++]].C / BK;
-        const uint32_t idesc = make_idesc(BN, p.src[ph.src[tap - 1]].fp16 != 0);
+        const uint32_t idesc = kb < ksw ? idesc_a : idesc_b;
         const int stage = kb % STAGES;
         const uint32_t parity = (uint32_t)((kb / STAGES) & 1);
         mbar_wait(&full_bar[stage], parity);

@@ -33,10 +33,13 @@ constexpr int PANEL_BYTES = BM * PANEL_COLS * 2;   // 128 rows x 128 bytes
 
 // MT = 128-row sub-tiles (accumulators) per tile: MT = 2 shares every weight tile between two
 // vertically adjacent row boxes, halving the weight traffic per MMA.
-template <int BN, int STAGES, int MT>
+// KS = 64-deep k-blocks per ring stage: with KS = 2 one full/empty barrier round trip (and one pass
+// of the MMA warp's wait / elect / commit path, ~200 ns of single-warp issue latency) covers twice
+// the MMA work, which is what bounds the narrow N tiles.
+template <int BN, int STAGES, int MT, int KS>
 struct PersistSmem {
   static constexpr int B_BYTES = BN * BK * 2;
-  static constexpr int STAGE_BYTES = MT * A_BYTES + B_BYTES;
+  static constexpr int STAGE_BYTES = KS * (MT * A_BYTES + B_BYTES);
   static constexpr int STAGING_OFF = STAGES * STAGE_BYTES;          // 2 panel buffers
   static constexpr int RED_OFF = STAGING_OFF + 2 * PANEL_BYTES;     // [8 sub-blocks][16 chunks] float2
   static constexpr int RED_BYTES = 2 * 8 * 16 * 8;   // double buffered
@@ -92,12 +95,12 @@ __device__ __forceinline__ WorkItem decode_item(int w, int total_tiles, int S) {
   return it;
 }
 
-template <int BN, int STAGES, int MT>
+template <int BN, int STAGES, int MT, int KS>
 __global__ void __launch_bounds__(P_THREADS, 1)
 tapgemm_persist_kernel(const __grid_constant__ TapGemmParams p, const __grid_constant__ CUtensorMap tmA0,
                        const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
                        const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut) {
-  using L = PersistSmem<BN, STAGES, MT>;
+  using L = PersistSmem<BN, STAGES, MT, KS>;
   // SWIZZLE_128B atoms need 1024-byte alignment; with no static shared memory the dynamic
   // window starts 1024-aligned (checked: a misaligned window traps instead of corrupting)
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -184,16 +187,20 @@ tapgemm_persist_kernel(const __grid_constant__ TapGemmParams p, const __grid_con
         const int cx = c.tx * p.bw * s.stride + ph.dx[t];
         const int cy = c.ty * (p.bh * MT) * s.stride + ph.dy[t];
         const int cb_img = s.bcast ? 0 : c.tb * p.bb;
-        for (int cb = 0; cb < ncb; ++cb, ++g) {
+        for (int cb = 0; cb < ncb; cb += KS, g += KS) {   // KS = 2: taps and splits hold whole pairs (host)
           if (g < kb0 || g >= kb1) continue;
           const uint32_t stage = it % STAGES;
           const uint32_t parity = (it / STAGES) & 1u;
           mbar_wait(&empty_bar[stage], parity ^ 1u);
           if (elect_one_sync()) {
             uint8_t* a_dst = smem + stage * L::STAGE_BYTES;
+            uint8_t* b_dst = a_dst + KS * MT * A_BYTES;
             mbar_expect_tx(&full_bar[stage], (uint32_t)L::STAGE_BYTES);
-            tma_load_4d(a_dst, tm, &full_bar[stage], cb * BK, cx, cy, cb_img);
-            tma_load_3d(a_dst + MT * A_BYTES, &tmB, &full_bar[stage], ph.w_k0 + g * BK, c.n0, wb);
+#pragma unroll
+            for (int u = 0; u < KS; ++u) {
+              tma_load_4d(a_dst + u * MT * A_BYTES, tm, &full_bar[stage], (cb + u) * BK, cx, cy, cb_img);
+              tma_load_3d(b_dst + u * L::B_BYTES, &tmB, &full_bar[stage], ph.w_k0 + (g + u) * BK, c.n0, wb);
+            }
           }
           __syncwarp();
           ++it;
@@ -210,30 +217,34 @@ tapgemm_persist_kernel(const __grid_constant__ TapGemmParams p, const __grid_con
       const int nkb_phase = ph.nkb;
       const int kb0 = (nkb_phase * wi.split) / S;
       const int nkb = (nkb_phase * (wi.split + 1)) / S - kb0;
-      int tap = 0, tap_end = 0;   // walks the taps along K: each tap's source fixes the operand format
+      const uint32_t idesc_a = make_idesc(BN, ph.fp16_first != 0), idesc_b = make_idesc(BN, ph.fp16_first == 0);
+      const int ksw = ph.kb_switch - kb0;   // operand format switches once along K at most
       const uint32_t buf = j & 1u;
       mbar_wait(&tempty_bar[buf], ((j >> 1) & 1u) ^ 1u);   // epilogue has drained this buffer
       tcgen05_fence_after();
       const uint32_t d_tmem = tmem_base + buf * (MT * BN);
-      for (int kb = 0; kb < nkb; ++kb, ++it) {
+      for (int kb = 0; kb < nkb; kb += KS, ++it) {
         const uint32_t stage = it % STAGES;
         const uint32_t parity = (it / STAGES) & 1u;
-        while (kb0 + kb >= tap_end) tap_end += p.src[ph.src[tap++]].C / BK;
-        const uint32_t idesc = make_idesc(BN, p.src[ph.src[tap - 1]].fp16 != 0);
+        const uint32_t idesc = kb < ksw ? idesc_a : idesc_b;   // KS = 2: the switch falls on a pair boundary (host)
         mbar_wait(&full_bar[stage], parity);
         tcgen05_fence_after();
         if (elect_one_sync()) {
           const uint32_t a_addr = smem_u32(smem + stage * L::STAGE_BYTES);
-          const uint64_t bdesc = make_smem_desc(a_addr + MT * A_BYTES);
+          const uint32_t b_addr = a_addr + KS * MT * A_BYTES;
 #pragma unroll
-          for (int m = 0; m < MT; ++m) {
-            const uint64_t adesc = make_smem_desc(a_addr + m * A_BYTES);
+          for (int u = 0; u < KS; ++u) {
+            const uint64_t bdesc = make_smem_desc(b_addr + u * L::B_BYTES);
 #pragma unroll
-            for (int k2 = 0; k2 < BK / 16; ++k2)
-              umma_bf16(d_tmem + m * BN, adesc + 2 * k2, bdesc + 2 * k2, idesc, (uint32_t)((kb | k2) != 0));
+            for (int m = 0; m < MT; ++m) {
+              const uint64_t adesc = make_smem_desc(a_addr + (u * MT + m) * A_BYTES);
+#pragma unroll
+              for (int k2 = 0; k2 < BK / 16; ++k2)
+                umma_bf16(d_tmem + m * BN, adesc + 2 * k2, bdesc + 2 * k2, idesc, (uint32_t)((kb | u | k2) != 0));
+            }
           }
           umma_commit(&empty_bar[stage]);
-          if (kb == nkb - 1) umma_commit(&tfull_bar[buf]);
+          if (kb + KS >= nkb) umma_commit(&tfull_bar[buf]);
         }
         __syncwarp();
       }
@@ -520,12 +531,12 @@ bool tapgemm_persist_eligible(const its_conv_desc* d, const TapGemmParams& p) {
   return true;
 }
 
-template <int BN, int STAGES, int MT>
+template <int BN, int STAGES, int MT, int KS>
 static int launch_persist(const TapGemmParams& p, const CUtensorMap* tmA, const CUtensorMap& tmB,
                           const CUtensorMap& tmOut, cudaStream_t stream) {
-  using L = PersistSmem<BN, STAGES, MT>;
+  using L = PersistSmem<BN, STAGES, MT, KS>;
   static_assert(L::TOTAL <= 227 * 1024, "shared memory budget");
-  auto kern = tapgemm_persist_kernel<BN, STAGES, MT>;
+  auto kern = tapgemm_persist_kernel<BN, STAGES, MT, KS>;
   static bool configured = false;
   if (!configured) {
     ITS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
@@ -594,15 +605,24 @@ int tapgemm_launch_persist(const its_conv_desc* d, const TapGemmParams& p, cudaS
     rc = encode_bf16_map(&tmOut, 5, p.out, dims, strides, box, estr, "output");
   }
   if (rc != ITS_OK) return rc;
+  // two k-blocks per ring stage when every tap, split and format switch covers whole pairs
+  bool pairs = (mt == 1 && bn <= 128 && d->cluster != 3);
+  for (int s = 0; s < p.nsrc && pairs; ++s) pairs = (p.src[s].C % (2 * BK) == 0);
+  for (int f = 0; f < p.nphases && pairs; ++f)
+    pairs = (p.phase[f].nkb % (2 * p.splits) == 0) && (p.phase[f].kb_switch % 2 == 0);
   if (mt == 2) {
-    if (bn == 64) return launch_persist<64, 4, 2>(pp, tmA, tmB, tmOut, stream);
-    return launch_persist<128, 4, 2>(pp, tmA, tmB, tmOut, stream);
+    if (bn == 64) return launch_persist<64, 4, 2, 1>(pp, tmA, tmB, tmOut, stream);
+    return launch_persist<128, 4, 2, 1>(pp, tmA, tmB, tmOut, stream);
+  }
+  if (pairs) {
+    if (bn == 64) return launch_persist<64, 4, 1, 2>(pp, tmA, tmB, tmOut, stream);
+    return launch_persist<128, 3, 1, 2>(pp, tmA, tmB, tmOut, stream);
   }
   switch (bn) {
-    case 64:  return launch_persist<64, 8, 1>(pp, tmA, tmB, tmOut, stream);
-    case 128: return launch_persist<128, 6, 1>(pp, tmA, tmB, tmOut, stream);
-    case 192: return launch_persist<192, 4, 1>(pp, tmA, tmB, tmOut, stream);
-    default:  return launch_persist<256, 4, 1>(pp, tmA, tmB, tmOut, stream);
+    case 64:  return launch_persist<64, 8, 1, 1>(pp, tmA, tmB, tmOut, stream);
+    case 128: return launch_persist<128, 6, 1, 1>(pp, tmA, tmB, tmOut, stream);
+    case 192: return launch_persist<192, 4, 1, 1>(pp, tmA, tmB, tmOut, stream);
+    default:  return launch_persist<256, 4, 1, 1>(pp, tmA, tmB, tmOut, stream);
   }
 }
 

@@ -14,6 +14,8 @@ struct DevSrc {
 struct DevPhase {
   int ntaps, w_k0, py, px;
   int nkb;                   // k-blocks of 64 in this phase
+  int fp16_first;            // operand format of k-blocks [0, kb_switch): 1 = IEEE fp16, 0 = bf16
+  int kb_switch;             // k-blocks [kb_switch, nkb) use the other format (nkb if none)
   int8_t src[ITS_MAX_TAPS], dy[ITS_MAX_TAPS], dx[ITS_MAX_TAPS];
 };
 
