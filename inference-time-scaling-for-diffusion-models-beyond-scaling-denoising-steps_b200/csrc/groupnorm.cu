@@ -259,7 +259,7 @@ struct GnStatArgs {
   float eps;
 };
 
-__global__ void __launch_bounds__(GN_THREADS) gn_apply_stats_kernel(const GnStatArgs a) {
+__global__ void __launch_bounds__(GN_THREADS, 4) gn_apply_stats_kernel(const GnStatArgs a) {
   __shared__ float s_mean[64], s_rstd[64];
   const int tid = threadIdx.x;
   const int chunk = blockIdx.x, img = blockIdx.y;
@@ -326,12 +326,14 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_stats_kernel(const GnStat
   }
   __syncthreads();
   if (!active) return;
-  float scale[8], shift[8];
+  float scale[8], shift[8], nscale[8], nshift[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int g = (cv * 8 + i) / cg;
     scale[i] = s_rstd[g] * gam[i];
     shift[i] = bet[i] - s_mean[g] * scale[i];
+    nscale[i] = -1.4426950408889634f * scale[i];
+    nshift[i] = -1.4426950408889634f * shift[i];
   }
   for (int pb = p0 + pl; pb < p1; pb += prow * U) {
     if (pb != p0 + pl) {
@@ -350,7 +352,14 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_stats_kernel(const GnStat
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const float v = fmaf(f[i], scale[i], shift[i]);
-          f[i] = a.silu ? silu_fast(v) : v;
+          if (a.silu) {
+            // v * rcp(1 + 2^(-v*log2e)); the exponent comes straight from the input (one FMA)
+            float e;
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fmaf(f[i], nscale[i], nshift[i])));
+            f[i] = __fdividef(v, 1.0f + e);
+          } else {
+            f[i] = v;
+          }
         }
         *reinterpret_cast<bf16x8*>(a.out + ((long long)img * a.HW + p) * a.C + cv * 8) = a.out_fp16 ? pack8_half(f) : pack8(f);
       }
@@ -444,8 +453,11 @@ extern "C" int its_group_norm_apply(void* out, const void* src0, int32_t C0, con
   a.st1 = reinterpret_cast<const float2*>(stats1);
   a.C0 = C0; a.C1 = C1; a.C = C; a.HW = HW; a.groups = groups; a.parts0 = parts0; a.parts1 = parts1;
   a.silu = silu; a.eps = eps; a.out_fp16 = out_fp16;
-  // ~32 KB of activations per CTA keeps >= 2 waves on 148 SMs for the large maps
+  // one wave: at most 4 CTAs per SM are resident (launch bounds), and every CTA repeats the
+  // statistics prologue of its image, so the grid is sized to fit the machine exactly once
   long long chunks = ((long long)HW * C * 2 + 32767) / 32768;
+  const long long fit = (4LL * 148) / n_img;
+  if (chunks > fit) chunks = fit;
   if (chunks < 1) chunks = 1;
   if (chunks > HW) chunks = HW;
   a.chunks = (int)chunks;
