@@ -79,29 +79,38 @@ __global__ void __launch_bounds__(256) head_patches_kernel(__nv_bfloat16* __rest
                                                            const float* __restrict__ x, long long nvec,
                                                            int n_img_in, int H, int Wd, int Cin) {
   pdl_prologue();
+  // per patch channel k: which term (0 hi, 1 lo, 2 hi, 3 zero) and which tap (ci, dy, dx); the
+  // table replaces ~10 integer divisions per element
+  __shared__ int8_t s_term[128], s_ci[128], s_dy[128], s_dx[128];
   const int K = Cin * 9;
+  if (threadIdx.x < 128) {
+    const int k = threadIdx.x;
+    const int term = k / K, t = k - term * K;
+    const int ci = t / 9, r = t - ci * 9, ky = r / 3, kx = r - ky * 3;
+    s_term[k] = (int8_t)(term < 3 ? term : 3);
+    s_ci[k] = (int8_t)ci; s_dy[k] = (int8_t)(ky - 1); s_dx[k] = (int8_t)(kx - 1);
+  }
+  __syncthreads();
+  const int HW = H * Wd;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec;
        i += (long long)gridDim.x * blockDim.x) {
     const int v = (int)(i & 15);
     const long long pix = i >> 4;
-    const int xw = (int)(pix % Wd);
-    const int y = (int)((pix / Wd) % H);
-    const int b = (int)(pix / ((long long)Wd * H));
-    const float* xin = x + (long long)(b % n_img_in) * Cin * H * Wd;
+    const int b = (int)(pix / HW);
+    const int rem = (int)(pix - (long long)b * HW);
+    const int y = rem / Wd, xw = rem - y * Wd;
+    const float* xin = x + (long long)(b % n_img_in) * Cin * HW;
     float f[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int k = v * 8 + j;
-      const int term = k / K, t = k - term * K;
+      const int term = s_term[k];
+      const int yy = y + s_dy[k], xx = xw + s_dx[k];
       float val = 0.f;
-      if (term < 3) {
-        const int ci = t / 9, r = t - ci * 9, ky = r / 3, kx = r - ky * 3;
-        const int yy = y + ky - 1, xx = xw + kx - 1;
-        if (yy >= 0 && yy < H && xx >= 0 && xx < Wd) {
-          const float xv = __ldg(xin + ((long long)ci * H + yy) * Wd + xx);
-          const float hi = __bfloat162float(__float2bfloat16_rn(xv));
-          val = (term == 1) ? xv - hi : hi;
-        }
+      if (term < 3 && yy >= 0 && yy < H && xx >= 0 && xx < Wd) {
+        const float xv = __ldg(xin + s_ci[k] * HW + yy * Wd + xx);
+        const float hi = __bfloat162float(__float2bfloat16_rn(xv));
+        val = (term == 1) ? xv - hi : hi;
       }
       f[j] = val;
     }
@@ -334,7 +343,7 @@ extern "C" int its_head_patches(void* out, const float* x, int32_t n_img, int32_
               "its_head_patches: unsupported shape Cin=%d (3 * 9 * Cin must fit 128 patch channels)", Cin);
   const long long nvec = (long long)n_img * H * Wd * 16;
   long long blocks = (nvec + 255) / 256;
-  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks > 148 * 8) blocks = 148 * 8;
   ITS_LAUNCH(head_patches_kernel, dim3((unsigned)blocks), dim3(256), 0, as_stream(stream),
              static_cast<__nv_bfloat16*>(out), x, nvec, n_img_in, H, Wd, Cin);
   return ITS_OK;
