@@ -390,5 +390,5 @@ extern "C" int its_conv_stats_parts(const its_conv_desc* desc_host) {
   TapGemmParams p;
   if (tapgemm_build_params(desc_host, &p, true) != ITS_OK) return 0;
   if (desc_host->schedule == 1 || !tapgemm_persist_eligible(desc_host, p)) return 0;
-  return tapgemm_stats_parts(p);
+  return tapgemm_stats_parts(desc_host, p);
 }

@@ -36,7 +36,7 @@ constexpr int PANEL_BYTES = BM * PANEL_COLS * 2;   // 128 rows x 128 bytes
 // KS = 64-deep k-blocks per ring stage: with KS = 2 one full/empty barrier round trip (and one pass
 // of the MMA warp's wait / elect / commit path, ~200 ns of single-warp issue latency) covers twice
 // the MMA work, which is what bounds the narrow N tiles.
-template <int BN, int STAGES, int MT, int KS>
+template <int BN, int STAGES, int MT, int KS, bool TM = false>
 struct PersistSmem {
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = KS * (MT * A_BYTES + B_BYTES);
@@ -48,6 +48,7 @@ struct PersistSmem {
   static constexpr int TOTAL = BAR_OFF + NBARS * 8 + 16;            // no slack: the window is 1024-aligned
   static constexpr int TMEM_COLS = (2 * MT * BN <= 128) ? 128 : (2 * MT * BN <= 256) ? 256 : 512;
   static_assert(2 * MT * BN <= 512, "TMEM holds two accumulator sets");
+  static_assert(!TM || (BN == 128 && MT == 2 && KS == 1), "transposed mode: 128 channels x 256 pixels");
 };
 
 struct TileCoord {
@@ -95,12 +96,18 @@ __device__ __forceinline__ WorkItem decode_item(int w, int total_tiles, int S) {
   return it;
 }
 
-template <int BN, int STAGES, int MT, int KS>
+// TM ("transposed accumulator", Cout tile of 128 with two row boxes): the MMA takes the WEIGHT tile as
+// its A operand (M = 128 channels) and the 256-pixel activation tile as its B operand (N = 256), so a
+// k-block is 4 instructions of N = 256 instead of 8 of N = 128 — measured, an N = 128 tcgen05.mma costs
+// ~98 clocks against its 64-clock floor while N = 256 runs at its 128-clock floor.  The accumulator is
+// then [channel lane][pixel column]; the epilogue transposes it through the swizzled staging panels
+// with 16-bit shared-memory stores, and the GroupNorm statistics become per-thread sums.
+template <int BN, int STAGES, int MT, int KS, bool TM>
 __global__ void __launch_bounds__(P_THREADS, 1)
 tapgemm_persist_kernel(const __grid_constant__ TapGemmParams p, const __grid_constant__ CUtensorMap tmA0,
                        const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
                        const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut) {
-  using L = PersistSmem<BN, STAGES, MT, KS>;
+  using L = PersistSmem<BN, STAGES, MT, KS, TM>;
   // SWIZZLE_128B atoms need 1024-byte alignment; with no static shared memory the dynamic
   // window starts 1024-aligned (checked: a misaligned window traps instead of corrupting)
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -144,7 +151,7 @@ tapgemm_persist_kernel(const __grid_constant__ TapGemmParams p, const __grid_con
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tfull_bar[b], 1);
       mbar_init(&tempty_bar[b], P_EPI_THREADS);
-      mbar_init(&pfull_bar[b], P_EPI_THREADS);
+      mbar_init(&pfull_bar[b], TM ? P_EPI_THREADS / 2 : P_EPI_THREADS);   // TM: 4 warps fill a panel
       mbar_init(&pempty_bar[b], 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -232,6 +239,14 @@ tapgemm_persist_kernel(const __grid_constant__ TapGemmParams p, const __grid_con
         if (elect_one_sync()) {
           const uint32_t a_addr = smem_u32(smem + stage * L::STAGE_BYTES);
           const uint32_t b_addr = a_addr + KS * MT * A_BYTES;
+          if constexpr (TM) {
+            // D[channel][pixel] += W[128 x 64] * Act[256 x 64]^T
+            const uint64_t wdesc = make_smem_desc(b_addr), xdesc = make_smem_desc(a_addr);
+            const uint32_t idesc_t = (idesc & ~(0x3Fu << 17)) | ((uint32_t)(256 >> 3) << 17);
+#pragma unroll
+            for (int k2 = 0; k2 < BK / 16; ++k2)
+              umma_bf16(d_tmem, wdesc + 2 * k2, xdesc + 2 * k2, idesc_t, (uint32_t)((kb | k2) != 0));
+          } else {
 #pragma unroll
           for (int u = 0; u < KS; ++u) {
             const uint64_t bdesc = make_smem_desc(b_addr + u * L::B_BYTES);
@@ -242,6 +257,7 @@ tapgemm_persist_kernel(const __grid_constant__ TapGemmParams p, const __grid_con
               for (int k2 = 0; k2 < BK / 16; ++k2)
                 umma_bf16(d_tmem + m * BN, adesc + 2 * k2, bdesc + 2 * k2, idesc, (uint32_t)((kb | u | k2) != 0));
             }
+          }
           }
           umma_commit(&empty_bar[stage]);
           if (kb + KS >= nkb) umma_commit(&tfull_bar[buf]);
@@ -318,6 +334,67 @@ tapgemm_persist_kernel(const __grid_constant__ TapGemmParams p, const __grid_con
           }
         }
         named_bar_sync(1, P_EPI_THREADS);
+      }
+      if constexpr (TM) {
+        // thread = (channel lane, 64-pixel quarter of the current row box); two rounds, one per row box
+        const int cglob = c.n0 + row;                 // output channel of this thread
+        const int bimg = c.tb;                        // bb == 1
+        float bvs = p.bias ? __ldg(p.bias + cglob) : 0.f;
+        if (p.vec) bvs += __ldg(p.vec + (long long)bimg * p.vec_stride + cglob);
+        if (p.vec2) bvs += __ldg(p.vec2 + (long long)bimg * p.vec2_stride + cglob);
+        mbar_wait(&tfull_bar[buf], (j >> 1) & 1u);
+        tcgen05_fence_after();
+        if (dbg != nullptr && et == 0 && j < 8) dbg[8 + j] = clock64();
+        const int pn = q >> 1;                        // 64-channel panel this warp's channels belong to
+        const uint32_t cc = (uint32_t)((q & 1) * 32 + lane);   // channel within the panel
+#pragma unroll 1
+        for (int m = 0; m < 2; ++m) {
+          const uint32_t P = pc + 2 * m + pn;         // global panel counter of (row box m, panel pn)
+          const uint32_t sb = P & 1u;
+          uint8_t* sbuf = staging + sb * PANEL_BYTES;
+          uint32_t v[64];
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * (MT * BN) +
+                                 (uint32_t)(m * 128 + half * 64);
+          tmem_ld32_nowait(taddr, v);
+          tmem_ld32_nowait(taddr + 32, v + 32);
+          mbar_wait(&pempty_bar[sb], ((P >> 1) & 1u) ^ 1u);
+          tmem_wait_ld();
+          if (m == 1) {
+            tcgen05_fence_before();
+            mbar_arrive(&tempty_bar[buf]);
+          }
+          float s = 0.f, qq = 0.f;
+          const uint32_t col_byte = (cc & 7u) * 2u;
+          const uint32_t chunk = cc >> 3;
+#pragma unroll
+          for (int i = 0; i < 64; ++i) {
+            const uint32_t prow = (uint32_t)(half * 64 + i);          // pixel row within the 128-row box
+            const float f = fmaf(__uint_as_float(v[i]), p.alpha, bvs);
+            const __nv_bfloat16 h = __float2bfloat16_rn(f);
+            const float r = __bfloat162float(h);
+            s += r;
+            qq = fmaf(r, r, qq);
+            const uint32_t dst = smem_u32(sbuf) + prow * 128u + (((chunk ^ (prow & 7u)) << 4) | col_byte);
+            asm volatile("st.shared.b16 [%0], %1;" ::"r"(dst), "h"(*reinterpret_cast<const unsigned short*>(&h)) : "memory");
+          }
+          fence_proxy_async_smem();
+          mbar_arrive(&pfull_bar[sb]);
+          if (p.stats != nullptr) {
+            s += __shfl_xor_sync(0xffffffffu, s, 1);
+            qq += __shfl_xor_sync(0xffffffffu, qq, 1);
+            s += __shfl_xor_sync(0xffffffffu, s, 2);
+            qq += __shfl_xor_sync(0xffffffffu, qq, 2);
+            if ((lane & 3) == 0) {
+              const int ty = c.ty * MT + m;
+              const int part = ((c.phase * tiles_img + ty * p.tiles_x + c.tx) << 1) + half;
+              reinterpret_cast<float2*>(p.stats)[((long long)bimg * p.stats_parts + part) * (p.Cout >> 2) + (cglob >> 2)] =
+                  make_float2(s, qq);
+            }
+          }
+        }
+        pc += 4;
+        if (dbg != nullptr && et == 0 && j < 8) dbg[24 + j] = clock64();
+        continue;
       }
       int b = c.tb * p.bb + rb;
       if (b >= p.B) b = p.B - 1;         // rows of a ragged last tile: values are never stored
@@ -511,13 +588,32 @@ int device_sm_count() {
   return n;
 }
 
-int tapgemm_stats_parts(const TapGemmParams& p) {
-  return p.nphases * (p.bb == 1 ? p.tiles_x * p.tiles_y : 1);
-}
-
 static int persist_bn(const its_conv_desc* d, const TapGemmParams& p) {
   if (d->bn != 0) return d->bn;
   return (p.Cout % 256 == 0) ? 256 : (p.Cout % 192 == 0) ? 192 : (p.Cout % 128 == 0) ? 128 : 64;
+}
+
+struct PersistCfg {
+  int bn, mt;
+  bool tm;      // transposed accumulator (128 channels x 256 pixels)
+};
+
+// Tile configuration of a layer on the persistent schedule.  d->cluster doubles as a tuning knob:
+// 1 = one row box per tile, 2 = two row boxes without the transposed accumulator.
+static PersistCfg persist_cfg(const its_conv_desc* d, const TapGemmParams& p) {
+  PersistCfg c;
+  c.bn = persist_bn(d, p);
+  // two row boxes per tile (shared weight tiles) when the N tile leaves TMEM room for two
+  // double-buffered accumulators and a tile of 2 x bh rows still tiles the image
+  c.mt = (c.bn <= 128 && p.bb == 1 && p.tiles_y % 2 == 0 && d->cluster != 1 && p.splits == 1) ? 2 : 1;
+  c.tm = (c.mt == 2 && c.bn == 128 && d->cluster != 2);
+  return c;
+}
+
+int tapgemm_stats_parts(const its_conv_desc* d, const TapGemmParams& p) {
+  // one slot per 128-row box of the image (two 64-pixel halves per box in transposed mode)
+  const PersistCfg c = persist_cfg(d, p);
+  return p.nphases * (p.bb == 1 ? p.tiles_x * p.tiles_y * (c.tm ? 2 : 1) : 1);
 }
 
 bool tapgemm_persist_eligible(const its_conv_desc* d, const TapGemmParams& p) {
@@ -531,12 +627,12 @@ bool tapgemm_persist_eligible(const its_conv_desc* d, const TapGemmParams& p) {
   return true;
 }
 
-template <int BN, int STAGES, int MT, int KS>
+template <int BN, int STAGES, int MT, int KS, bool TM = false>
 static int launch_persist(const TapGemmParams& p, const CUtensorMap* tmA, const CUtensorMap& tmB,
                           const CUtensorMap& tmOut, cudaStream_t stream) {
-  using L = PersistSmem<BN, STAGES, MT, KS>;
+  using L = PersistSmem<BN, STAGES, MT, KS, TM>;
   static_assert(L::TOTAL <= 227 * 1024, "shared memory budget");
-  auto kern = tapgemm_persist_kernel<BN, STAGES, MT, KS>;
+  auto kern = tapgemm_persist_kernel<BN, STAGES, MT, KS, TM>;
   static bool configured = false;
   if (!configured) {
     ITS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
@@ -564,11 +660,10 @@ int tapgemm_launch_persist(const its_conv_desc* d, const TapGemmParams& p, cudaS
   ITS_REQUIRE(p.w_pitch % 8 == 0 && (reinterpret_cast<uintptr_t>(p.w) & 15) == 0, "its_conv_igemm: weight alignment");
   ITS_REQUIRE((reinterpret_cast<uintptr_t>(p.out) & 15) == 0, "its_conv_igemm: output pointer alignment");
   if (p.stats != nullptr)
-    ITS_REQUIRE(p.stats_parts == tapgemm_stats_parts(p), "its_conv_igemm: stats_parts=%d, the tiling writes %d",
-                p.stats_parts, tapgemm_stats_parts(p));
-  // two row boxes per tile (shared weight tiles) when the N tile leaves TMEM room for two
-  // double-buffered accumulators and a tile of 2 x bh rows still tiles the image
-  const int mt = (bn <= 128 && p.bb == 1 && p.tiles_y % 2 == 0 && d->cluster != 1 && p.splits == 1) ? 2 : 1;
+    ITS_REQUIRE(p.stats_parts == tapgemm_stats_parts(d, p), "its_conv_igemm: stats_parts=%d, the tiling writes %d",
+                p.stats_parts, tapgemm_stats_parts(d, p));
+  const PersistCfg cfg = persist_cfg(d, p);
+  const int mt = cfg.mt;
   TapGemmParams pp = p;
   if (p.splits > 1) {
     // workspace: [flags: one int per (tile, partial split), padded to 64 words][partials fp32]
@@ -612,6 +707,7 @@ int tapgemm_launch_persist(const its_conv_desc* d, const TapGemmParams& p, cudaS
     pairs = (p.phase[f].nkb % (2 * p.splits) == 0) && (p.phase[f].kb_switch % 2 == 0);
   if (mt == 2) {
     if (bn == 64) return launch_persist<64, 4, 2, 1>(pp, tmA, tmB, tmOut, stream);
+    if (cfg.tm) return launch_persist<128, 4, 2, 1, true>(pp, tmA, tmB, tmOut, stream);
     return launch_persist<128, 4, 2, 1>(pp, tmA, tmB, tmOut, stream);
   }
   if (pairs) {

@@ -58,7 +58,7 @@ int tapgemm_launch_sm100(const its_conv_desc* d, const TapGemmParams& p, cudaStr
 bool tapgemm_persist_eligible(const its_conv_desc* d, const TapGemmParams& p);
 int tapgemm_launch_persist(const its_conv_desc* d, const TapGemmParams& p, cudaStream_t stream);
 // number of GroupNorm partial-sum slots per image the persistent kernel writes for this tiling
-int tapgemm_stats_parts(const TapGemmParams& p);
+int tapgemm_stats_parts(const its_conv_desc* d, const TapGemmParams& p);
 int encode_bf16_map(CUtensorMap* tm, int rank, const void* base, const cuuint64_t* dims,
                     const cuuint64_t* strides_bytes, const cuuint32_t* box, const cuuint32_t* estr,
                     const char* what);
