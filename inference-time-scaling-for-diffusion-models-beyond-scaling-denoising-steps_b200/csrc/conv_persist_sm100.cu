@@ -483,8 +483,8 @@ tapgemm_persist_kernel(const __grid_constant__ TapGemmParams p, const __grid_con
         }
         fence_proxy_async_smem();
         mbar_arrive(&pfull_bar[sb]);
-        mbar_wait(&pfull_bar[sb], spar);         // every thread's part of the panel is staged
         if (p.stats != nullptr) {
+          mbar_wait(&pfull_bar[sb], spar);       // every thread's part of the panel is staged
           if (prev_dst != nullptr) {             // final reduce of the previous panel's sub-block sums
             const float2* rd = red + ((pc + 1) & 1u) * 128;
             float S = 0.f, Q = 0.f;

@@ -69,6 +69,26 @@ def test_unet_forward_is_batch_invariant_and_deterministic(cuda_dev):
     assert torch.equal(full, halves)
 
 
+def test_unet_forward_batch_invariance_across_schedules(cuda_dev):
+    """Large, ragged population: the split-K layers exceed the resident-CTA budget of the persistent
+    schedule and fall back to the tile-per-CTA kernel with the same split order, the last tile of every
+    multi-image box is ragged — a candidate's eps must still be bit-identical to the small-batch run."""
+    cfg = cases.FORWARD_CASES["u_3lvl"]
+    net, _ = build_shell(cfg, cuda_dev)
+    x, t, _ = cases.forward_inputs(cfg)
+    x, t = x.to(cuda_dev), t.to(cuda_dev)
+    small = net(x, t)
+    g = torch.Generator().manual_seed(7)
+    n_big = 301
+    xb = torch.randn(n_big, *x.shape[1:], generator=g).to(cuda_dev)
+    tb = torch.randint(0, cfg["T"], (n_big,), generator=g).to(cuda_dev)
+    xb[5:5 + x.shape[0]] = x
+    tb[5:5 + x.shape[0]] = t
+    big = net(xb, tb)
+    assert torch.isfinite(big).all()
+    assert torch.equal(big[5:5 + x.shape[0]], small)
+
+
 @pytest.mark.parametrize("name", ["u_small_T20", "c_small_T20"])
 @pytest.mark.parametrize("graph", [False, True], ids=["eager", "cudagraph"])
 def test_sampler_injected_noise_vs_reference(cuda_dev, name, graph):
