@@ -43,8 +43,9 @@ extern "C" {
 int its_version(void);                     /* 10000*major + 100*minor + patch */
 const char* its_last_error_string(void);   /* per-thread, never NULL          */
 int its_device_sm_count(int* out_host);    /* cudaDevAttrMultiProcessorCount  */
-int its_set_pdl(int32_t enabled);         /* programmatic dependent launch on
-                                              every kernel (default 1; env ITS_PDL) */
+int its_set_pdl(int32_t mode);            /* programmatic dependent launch: 0 off,
+                                              1 every launch, 2 small kernels, 3
+                                              tap-GEMMs only (default; env ITS_PDL) */
 int its_abi_sizeof(int which);             /* 0: its_conv_desc, 1: its_src_t,
                                               2: its_phase_t (binding self-check) */
 

@@ -428,7 +428,7 @@ static int launch_variant(const TapGemmParams& p, const CUtensorMap* tmA, const 
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = pdl_enabled() ? 2 : 1;
+  cfg.numAttrs = pdl_enabled(1) ? 2 : 1;
   ITS_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, p, tmA[0], tmA[1], tmA[2], tmB));
   if (p.splits > 1) {
     const long long items = (long long)p.B * p.Hm * p.Wm * (p.Cout / 8) * p.nphases;

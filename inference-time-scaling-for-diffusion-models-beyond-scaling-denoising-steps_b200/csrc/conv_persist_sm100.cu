@@ -649,7 +649,7 @@ static int launch_persist(const TapGemmParams& p, const CUtensorMap* tmA, const 
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cfg.numAttrs = pdl_enabled(1) ? 1 : 0;
   ITS_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, p, tmA[0], tmA[1], tmA[2], tmB, tmOut));
   return ITS_OK;
 }

@@ -35,8 +35,9 @@ static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStre
 // Programmatic dependent launch: every kernel of the library starts with pdl_prologue()
 // (release the next launch, then wait for the previous grid's memory to be visible), so
 // consecutive launches on a stream overlap their launch latency / set-up with the tail of
-// the predecessor.  its_set_pdl(0) turns the launch attribute off (plain stream order).
-bool pdl_enabled();
+// the predecessor — when the launch carries the attribute (its_set_pdl / ITS_PDL; by default only the
+// tap-GEMM launches do, see the measurements in ddpm_step.cu).
+bool pdl_enabled(int kind = 0);   // kind: 0 = small kernel, 1 = tap-GEMM
 __device__ __forceinline__ void pdl_prologue() {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   asm volatile("griddepcontrol.wait;" ::: "memory");
