@@ -169,51 +169,67 @@ tapgemm_persist_kernel(const __grid_constant__ TapGemmParams p, const __grid_con
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  // everything above overlaps the tail of the previous kernel under programmatic dependent
-  // launch; nothing below may touch global memory before the producer grid has finished
-  pdl_prologue();
+  // Everything above overlaps the tail of the previous kernel under programmatic dependent launch.
+  // Nothing below may touch memory the previous kernel writes before griddepcontrol.wait — the
+  // producer warp uses the slack to request the WEIGHT tiles of its first ring round (weights are
+  // never written on the device), every other thread waits right away.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  if (warp != 0) asm volatile("griddepcontrol.wait;" ::: "memory");
   if (dbg != nullptr && threadIdx.x == 0) dbg[2] = clock64();
 
   if (warp == 0) {
     // ------------------------------------------------ TMA producer ----
     // converged warp; one elected lane issues the loads of a stage
-    uint32_t it = 0;   // k-blocks issued so far (ring position)
-    for (int w = blockIdx.x; w < total_items; w += gridDim.x) {
-      const WorkItem wi = decode_item(w, total_tiles, S);
-      const TileCoord c = decode_tile(p, wi.tile, tiles_m, tiles_n, BN, MT);
-      const DevPhase& ph = p.phase[c.phase];
-      const int kb0 = (ph.nkb * wi.split) / S, kb1 = (ph.nkb * (wi.split + 1)) / S;
-      const int wb = (p.w_batch_stride != 0) ? c.tb * p.bb : 0;   // per-image B operand (attention)
-      int g = 0;
-      for (int t = 0; t < ph.ntaps && g < kb1; ++t) {
-        const int si = ph.src[t];
-        const DevSrc& s = p.src[si];
-        const int ncb = s.C / BK;
-        if (g + ncb <= kb0) { g += ncb; continue; }
-        const CUtensorMap* tm = (si == 0) ? &tmA0 : (si == 1) ? &tmA1 : &tmA2;
-        const int cx = c.tx * p.bw * s.stride + ph.dx[t];
-        const int cy = c.ty * (p.bh * MT) * s.stride + ph.dy[t];
-        const int cb_img = s.bcast ? 0 : c.tb * p.bb;
-        for (int cb = 0; cb < ncb; cb += KS, g += KS) {   // KS = 2: taps and splits hold whole pairs (host)
-          if (g < kb0 || g >= kb1) continue;
-          const uint32_t stage = it % STAGES;
-          const uint32_t parity = (it / STAGES) & 1u;
-          mbar_wait(&empty_bar[stage], parity ^ 1u);
-          if (elect_one_sync()) {
-            uint8_t* a_dst = smem + stage * L::STAGE_BYTES;
-            uint8_t* b_dst = a_dst + KS * MT * A_BYTES;
-            mbar_expect_tx(&full_bar[stage], (uint32_t)L::STAGE_BYTES);
+    uint32_t npre = 0;   // ring stages whose weight tiles were requested before the wait
+    auto produce = [&](const bool pre) {
+      uint32_t it = 0;   // k-blocks issued so far (ring position)
+      for (int w = blockIdx.x; w < total_items; w += gridDim.x) {
+        const WorkItem wi = decode_item(w, total_tiles, S);
+        const TileCoord c = decode_tile(p, wi.tile, tiles_m, tiles_n, BN, MT);
+        const DevPhase& ph = p.phase[c.phase];
+        const int kb0 = (ph.nkb * wi.split) / S, kb1 = (ph.nkb * (wi.split + 1)) / S;
+        const int wb = (p.w_batch_stride != 0) ? c.tb * p.bb : 0;   // per-image B operand (attention)
+        int g = 0;
+        for (int t = 0; t < ph.ntaps && g < kb1; ++t) {
+          const int si = ph.src[t];
+          const DevSrc& s = p.src[si];
+          const int ncb = s.C / BK;
+          if (g + ncb <= kb0) { g += ncb; continue; }
+          const CUtensorMap* tm = (si == 0) ? &tmA0 : (si == 1) ? &tmA1 : &tmA2;
+          const int cx = c.tx * p.bw * s.stride + ph.dx[t];
+          const int cy = c.ty * (p.bh * MT) * s.stride + ph.dy[t];
+          const int cb_img = s.bcast ? 0 : c.tb * p.bb;
+          for (int cb = 0; cb < ncb; cb += KS, g += KS) {   // KS = 2: taps and splits hold whole pairs (host)
+            if (g < kb0 || g >= kb1) continue;
+            if (pre && it >= (uint32_t)STAGES) { npre = it; return; }
+            const uint32_t stage = it % STAGES;
+            const uint32_t parity = (it / STAGES) & 1u;
+            if (!pre) mbar_wait(&empty_bar[stage], parity ^ 1u);
+            if (elect_one_sync()) {
+              uint8_t* a_dst = smem + stage * L::STAGE_BYTES;
+              uint8_t* b_dst = a_dst + KS * MT * A_BYTES;
+              if (pre || it >= npre) {
+                mbar_expect_tx(&full_bar[stage], (uint32_t)L::STAGE_BYTES);
 #pragma unroll
-            for (int u = 0; u < KS; ++u) {
-              tma_load_4d(a_dst + u * MT * A_BYTES, tm, &full_bar[stage], (cb + u) * BK, cx, cy, cb_img);
-              tma_load_3d(b_dst + u * L::B_BYTES, &tmB, &full_bar[stage], ph.w_k0 + (g + u) * BK, c.n0, wb);
+                for (int u = 0; u < KS; ++u)
+                  tma_load_3d(b_dst + u * L::B_BYTES, &tmB, &full_bar[stage], ph.w_k0 + (g + u) * BK, c.n0, wb);
+              }
+              if (!pre) {
+#pragma unroll
+                for (int u = 0; u < KS; ++u)
+                  tma_load_4d(a_dst + u * MT * A_BYTES, tm, &full_bar[stage], (cb + u) * BK, cx, cy, cb_img);
+              }
             }
+            __syncwarp();
+            ++it;
           }
-          __syncwarp();
-          ++it;
         }
       }
-    }
+      if (pre) npre = it;
+    };
+    if (p.w_batch_stride == 0) produce(true);
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    produce(false);
   } else if (warp == 1) {
     // ------------------------------------------------- MMA issuer -----
     // the whole warp walks the loop (converged waits), one elected lane issues
