@@ -272,6 +272,15 @@ int its_attention_fused(void* out, const void* qk, const void* vT,
                         const float* bias_v, int32_t n_img, int32_t N, int32_t C,
                         float scale, void* stream);
 
+/* Streaming attention core for maps with more tokens than one TMEM score tile holds
+ * (ModelCondition.py:108-113 on 32x32 maps: N = 1024, C = 128): same operands and
+ * result as its_attention_fused, keys processed in blocks of 128 with a running
+ * row maximum / row sum (fp32); scores and probabilities stay on chip.
+ * N a multiple of 128, >= 256; C = 64 or 128.                                 */
+int its_attention_flash(void* out, const void* qk, const void* vT,
+                        const float* bias_v, int32_t n_img, int32_t N, int32_t C,
+                        float scale, void* stream);
+
 /* ------------------------------------------------------------------------
  * Verifiers and selection.
  *   its_image_stats: per image mean, unbiased variance, min and the L2-

@@ -119,6 +119,7 @@ class SamplerBase(nn.Module):
             if self.guided:
                 lab = labels.reshape(-1).to(device=x_T.device, dtype=torch.int64)
                 plan.labels.copy_(torch.cat([lab, torch.zeros_like(lab)]))
+                plan.run_label_ops()      # label embedding -> cond_proj vectors: once per trajectory
             if noise is not None:
                 if noise.shape[0] != self.T or tuple(noise.shape[1:]) != tuple(x_T.shape):
                     raise ValueError("injected noise must be [T, *x_T.shape]; entry t is used at time_step t")

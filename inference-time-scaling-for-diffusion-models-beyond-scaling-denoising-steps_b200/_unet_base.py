@@ -58,5 +58,6 @@ class PlannedUNet(nn.Module):
             p.t_idx.copy_(t.reshape(-1).to(torch.int64))
             if labels is not None:
                 p.labels.copy_(labels.reshape(-1).to(torch.int64))
+        p.run_label_ops()
         p.run()
         return p.eps.clone()

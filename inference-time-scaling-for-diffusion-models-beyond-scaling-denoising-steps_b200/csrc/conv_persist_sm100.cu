@@ -73,8 +73,9 @@ __device__ __forceinline__ TileCoord decode_tile(const TapGemmParams& p, int til
 }
 
 // Split-K work items: item w of total_tiles * S.  All partial items (split s < S-1) come first,
-// the owner items (s = S-1, which reduce and run the epilogue) last, so that with the static
-// round-robin schedule an owner never waits for work queued behind another waiting owner.
+// the owner items (s = S-1, which reduce and run the epilogue) last.  CTA c walks items c, c + grid,
+// ... in increasing order, so on every CTA all partial items precede all owner items: a partial item
+// (which never waits) is never queued behind a waiting owner, for any number of rounds.
 struct WorkItem {
   int tile, split;
 };
@@ -691,7 +692,10 @@ int tapgemm_launch_persist(const its_conv_desc* d, const TapGemmParams& p, cudaS
                 (long long)d->ws_elems, need);
     for (int f = 0; f < p.nphases; ++f)
       ITS_REQUIRE(p.splits <= p.phase[f].nkb, "its_conv_igemm: splits=%d exceeds the %d k-blocks of phase %d", p.splits, p.phase[f].nkb, f);
-    ITS_REQUIRE(tiles * p.splits <= device_sm_count(), "its_conv_igemm: %lld split-K work items exceed the %d resident CTAs", tiles * p.splits, device_sm_count());
+    // No limit on tiles * splits: the static round-robin schedule hands CTA c the items c, c + grid,
+    // c + 2 grid, ... in increasing order and every partial item precedes every owner item in that
+    // order, so no partial item is ever queued behind a (possibly waiting) owner on any CTA; partial
+    // items never wait, hence every owner's spin terminates whatever the number of rounds.
     pp.ws_flag_words = (int)nflag;
   }
   CUtensorMap tmA[ITS_MAX_SRC], tmB, tmOut;

@@ -59,6 +59,52 @@ __global__ void __launch_bounds__(256) linear_kernel(float* __restrict__ y, cons
   }
 }
 
+// Same sums for R rows at a time: the activated input rows are staged once per CTA in shared
+// memory and every weight row is read once per R rows instead of once per row (the label
+// projections of the conditional net have one row per image).  Per (b, n) the summation order is
+// the one of linear_kernel (lane-strided over K, then the shuffle tree), so results are bit-identical.
+template <int R>
+__global__ void __launch_bounds__(256) linear_rows_kernel(float* __restrict__ y, const float* __restrict__ x,
+                                                          const float* __restrict__ W,
+                                                          const float* __restrict__ bias, int n_rows, int K,
+                                                          int N, int silu_in, int silu_out, int accumulate,
+                                                          int cols_per_block) {
+  extern __shared__ float xs[];   // [R][K]
+  pdl_prologue();
+  const int b0 = blockIdx.y * R;
+  for (int i = threadIdx.x; i < R * K; i += blockDim.x) {
+    const int r = i / K, k = i - r * K;
+    float xv = (b0 + r < n_rows) ? x[(long long)(b0 + r) * K + k] : 0.f;
+    if (silu_in) xv = xv / (1.0f + expf(-xv));
+    xs[i] = xv;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_end = min(N, (int)(blockIdx.x + 1) * cols_per_block);
+  for (int n = blockIdx.x * cols_per_block + warp; n < n_end; n += 8) {
+    const float* wr = W + (long long)n * K;
+    float acc[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) acc[r] = 0.f;
+    for (int k = lane; k < K; k += 32) {
+      const float wv = __ldg(wr + k);
+#pragma unroll
+      for (int r = 0; r < R; ++r) acc[r] = fmaf(xs[r * K + k], wv, acc[r]);
+    }
+    const float bn = bias ? bias[n] : 0.f;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const float a = warp_sum(acc[r]);
+      if (lane == 0 && b0 + r < n_rows) {
+        float v = a + bn;
+        if (silu_out) v = v / (1.0f + expf(-v));
+        float* dst = y + (long long)(b0 + r) * N + n;
+        *dst = accumulate ? (*dst + v) : v;
+      }
+    }
+  }
+}
+
 }  // namespace its
 
 extern "C" int its_time_embed(float* out, const int64_t* t_idx, const int32_t* t_dev,
@@ -88,6 +134,21 @@ extern "C" int its_linear(float* y, const float* x, const float* W, const float*
                           int32_t accumulate, void* stream) {
   ITS_REQUIRE(y && x && W, "its_linear: null pointer");
   ITS_REQUIRE(n_rows > 0 && K > 0 && N > 0, "its_linear: bad sizes");
+  if (n_rows > 1 && (long long)K * 16 * 4 <= 48 * 1024) {
+    // row-blocked variant: 64 output columns per CTA
+    const int cpb = 64;
+    if (n_rows > 8) {
+      ITS_LAUNCH(its::linear_rows_kernel<16>, dim3((N + cpb - 1) / cpb, (n_rows + 15) / 16), dim3(256),
+                 (size_t)K * 16 * 4, its::as_stream(stream), y, x, W, bias, n_rows, K, N, silu_in, silu_out,
+                 accumulate, cpb);
+    } else {
+      ITS_LAUNCH(its::linear_rows_kernel<4>, dim3((N + cpb - 1) / cpb, (n_rows + 3) / 4), dim3(256),
+                 (size_t)K * 4 * 4, its::as_stream(stream), y, x, W, bias, n_rows, K, N, silu_in, silu_out,
+                 accumulate, cpb);
+    }
+    ITS_CHECK_LAUNCH();
+    return ITS_OK;
+  }
   const long long warps = (long long)n_rows * N;
   const long long blocks = (warps * 32 + 255) / 256;
   ITS_REQUIRE(blocks < (1LL << 31), "its_linear: too large");

@@ -68,6 +68,8 @@ class UNetPlan:
         self.keep: List[torch.Tensor] = []      # everything the launches point into
         self.descs: List[ConvDesc] = []
         self.ops: List[Tuple] = []
+        self.label_ops: List[Tuple] = []         # label embedding -> cond_proj of every ResBlock
+        self.n_label_launches = 0
         self.op_info: List[Tuple[str, int, int]] = []   # (kind, algorithmic flops, launches) per op
         self.n_launches = 0
         self.flops = 0                           # algorithmic 2*MAC of the tensor-core GEMMs + linears
@@ -85,6 +87,7 @@ class UNetPlan:
         self.n_img, self.H, self.W, self.n_img_in = int(n_img), 0, 0, int(n_img)
         self.uniform_t, self.dev, self.impl_forced = False, torch.device(device), impl
         self.keep, self.descs, self.ops, self.op_info = [], [], [], []
+        self.label_ops, self.n_label_launches = [], 0
         self.n_launches, self.flops = 0, 0
         self.gn_partials, self.tproj, self.cproj = None, None, None
         self.ws, self.split_k = None, True
@@ -106,6 +109,11 @@ class UNetPlan:
         return t
 
     def _op(self, fn, *args, launches: int = 1, flops: int = 0, kind: str = "other"):
+        if getattr(self, "_into_label_ops", False):
+            # depends on the labels only (constant over a trajectory): see run_label_ops()
+            self.label_ops.append((fn, args))
+            self.n_label_launches += launches
+            return
         self.ops.append((fn, args))
         self.op_info.append((kind, flops, launches))
         self.n_launches += launches
@@ -237,8 +245,6 @@ class UNetPlan:
         bn, splits = 0, 1
         if persistent and self.split_k:
             bn, splits = self._persist_plan(Hm, Wm, cout, len(phases), nkb_min + (cout // 64 if can_fold else 0))
-            if splits > 1 and self._tiles_at(B, Hm, Wm) * (cout // bn) * len(phases) * splits > self.sm_count:
-                persistent = False          # more split-K work items than resident CTAs at this batch
         if persistent:
             if can_fold:
                 # identity shortcut as one more K block with identity weights (exact: 1.0 * bf16 value
@@ -396,12 +402,15 @@ class UNetPlan:
             wv_img = self._hold(wv.reshape(1, 1, Cc, Cc), a.dtype)
             vT = self.conv([(wv_img, Cc, 0, 1, True)], [(one, 0, 0, 0)], 1, Cc, a.view(B, N, Cc), N,
                            w_batch_stride=N * Cc, out_shape=(B, 1, Cc, N), want_stats=False)
-            if N == 256 and Cc % 64 == 0 and Cc <= 384 and self._impl_for([Cc], Cc) == 0 and self.fused_attention:
+            fused256 = N == 256 and Cc % 64 == 0 and Cc <= 384
+            flash = N % 128 == 0 and N > 256 and Cc in (64, 128)
+            if (fused256 or flash) and self._impl_for([Cc], Cc) == 0 and self.fused_attention:
                 # scores in TMEM, probabilities in shared memory: one launch for QK^T, softmax and PV
                 o = self._new((B, H, W, Cc))
                 bvh = self._hold(bv, torch.float32)
-                self._op(self.L.its_attention_fused, o.data_ptr(), qk.data_ptr(), vT.data_ptr(), bvh.data_ptr(), B, N,
-                         Cc, scale, flops=4 * B * N * N * Cc, kind="attention_fused")
+                self._op(self.L.its_attention_fused if fused256 else self.L.its_attention_flash, o.data_ptr(),
+                         qk.data_ptr(), vT.data_ptr(), bvh.data_ptr(), B, N, Cc, scale, flops=4 * B * N * N * Cc,
+                         kind="attention_fused" if fused256 else "attention_flash")
                 wp = self._hold(at.proj.weight.detach().float()[:, :, 0, 0], torch.float32)
                 bp = self._hold(at.proj.bias, torch.float32)
                 return self.conv([(o, Cc, 0, 1, False)], [(one, 0, 0, 0)], H, W, wp, Cc, bias=bp, res=x)
@@ -549,8 +558,12 @@ class UNetPlan:
         bt = self._hold(torch.cat([rb.temb_proj[1].bias.detach().float() for rb in blocks], 0), torch.float32)
         self.tproj = self.linear(temb, wt, bt, silu_in=True)
         self.cproj = None
-        self._label_ops_start = None
         if self.cond:
+            # Everything from the label embedding to the per-ResBlock cond_proj vectors is a function of
+            # the labels alone (ModelCondition.py:216,131-135,154).  The labels of a trajectory never
+            # change, so the sampler runs these launches once per forward() instead of once per step;
+            # UNet.forward() runs them on every call.
+            self._into_label_ops = True
             ce = m.cond_embedding.condEmbedding
             ctab = self._hold(ce[0].weight, torch.float32)
             cemb0 = self._new((B, ch), torch.float32)
@@ -562,6 +575,7 @@ class UNetPlan:
             wc = self._hold(torch.cat([rb.cond_proj[1].weight.detach().float() for rb in blocks], 0), torch.float32)
             bc = self._hold(torch.cat([rb.cond_proj[1].bias.detach().float() for rb in blocks], 0), torch.float32)
             self.cproj = self.linear(cemb, wc, bc, silu_in=True)
+            self._into_label_ops = False
         # ---- head
         h = self.head_conv(m.head.weight, m.head.bias, self.x_in, B, H, W)
         hs = [h]
@@ -592,6 +606,15 @@ class UNetPlan:
                      a.shape[2], ct, 3, flops=2 * B * H * W * 3 * 9 * ct, kind="conv_tail")
 
     # ---------------------------------------------------------------- run --
+    def run_label_ops(self) -> None:
+        """Enqueue the launches that depend on `self.labels` only (conditional net; no-op otherwise).
+        Must run after every change of the labels and before run()."""
+        s = _lib.stream_ptr()
+        for fn, args in self.label_ops:
+            rc = fn(*args, s)
+            if rc != 0:
+                _lib.check(rc, fn.__name__)
+
     def run(self) -> None:
         """Enqueue every launch on the current stream (graph-capturable)."""
         s = _lib.stream_ptr()

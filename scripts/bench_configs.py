@@ -31,6 +31,7 @@ for name in ("A", "C", "E"):
     plan.t_dev.fill_(T // 2)
     if plan.labels is not None:
         plan.labels.copy_(torch.cat([1 + torch.arange(a.candidates) % 10, torch.zeros(a.candidates, dtype=torch.long)]).to(dev))
+    plan.run_label_ops()     # label embedding -> cond_proj: once per trajectory (labels never change inside one)
     for _ in range(3):
         plan.run()
     torch.cuda.synchronize()

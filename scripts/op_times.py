@@ -16,13 +16,21 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=64)
 ap.add_argument("--img", type=int, default=32)
 ap.add_argument("--reps", type=int, default=20)
+ap.add_argument("--cond", action="store_true", help="config C: ModelCondition.UNet, batch = 2 x candidates (CFG)")
 a = ap.parse_args()
 torch.manual_seed(0)
 dev = torch.device("cuda:0")
-net = UNet(T=1000, ch=128, ch_mult=[1, 2, 3, 4], attn=[1] if a.img == 32 else [2], num_res_blocks=2, dropout=0.15).to(dev).eval()
+if a.cond:
+    from its_b200.DiffusionFreeGuidence import UNet as CUNet
+    net = CUNet(T=1000, num_labels=10, ch=128, ch_mult=[1, 2, 3, 4], num_res_blocks=2, dropout=0.15).to(dev).eval()
+else:
+    net = UNet(T=1000, ch=128, ch_mult=[1, 2, 3, 4], attn=[1] if a.img == 32 else [2], num_res_blocks=2, dropout=0.15).to(dev).eval()
 plan = net.plan(a.batch, a.img, a.img, n_img_in=a.batch, uniform_t=True)
 plan.x_in.normal_()
 plan.t_dev.fill_(500)
+if plan.labels is not None:
+    plan.labels.copy_((torch.arange(a.batch) % 11).to(dev))
+plan.run_label_ops()
 for _ in range(3):
     plan.run()
 torch.cuda.synchronize()

@@ -370,6 +370,35 @@ def test_split_k_matches_unsplit_bitwise_inputs(cuda_dev, built_lib):
     check_close(nchw(outs[0]), nchw(outs[1]), 8e-3, "split vs unsplit")   # fp32 re-association + bf16 rounding
 
 
+def test_persistent_split_k_with_more_work_items_than_sms(cuda_dev, built_lib):
+    """Persistent split-K at a batch whose work items (tiles x splits) exceed the resident CTAs: partial
+    items precede owner items on every CTA, so owners never starve (conv_persist_sm100.cu); the
+    result is bit-identical to the same images evaluated in a small batch (fixed summation order)."""
+    from its_b200.engine import UNetPlan, pack_conv_weight, taps_square
+    g = torch.Generator().manual_seed(9)
+    B, H, C = 160, 4, 512
+    x = torch.randn(B, C, H, H, generator=g).to(cuda_dev)
+    w = (torch.randn(C, C, 3, 3, generator=g) / 68).to(cuda_dev)
+    xin, wp = nhwc(x), pack_conv_weight(w).contiguous()
+    plan = UNetPlan.scratch(cuda_dev, B, 0)
+    out = plan.conv([(xin, C, 0, 1, False)], [(taps_square(3), 0, 0, 0)], H, H, wp, C)
+    d = plan.descs[0]
+    assert d.splits > 1 and d.schedule != 1 and d.stats_parts > 0     # persistent, split, statistics kept
+    assert (B // 8) * (C // d.bn) * d.splits > 148
+    for _ in range(3):            # flags are self-cleaning: repeated launches give the same answer
+        plan.run()
+    torch.cuda.synchronize()
+    ref = F.conv2d(bf(x), bf(w), None, padding=1)
+    check_close(nchw(out), ref, 6e-3, "large-batch split")
+    small = UNetPlan.scratch(cuda_dev, 8, 0)
+    xs = xin[:8].contiguous()
+    out8 = small.conv([(xs, C, 0, 1, False)], [(taps_square(3), 0, 0, 0)], H, H, wp, C)
+    small.run()
+    torch.cuda.synchronize()
+    assert small.descs[0].splits == d.splits
+    assert torch.equal(out8, out[:8])
+
+
 class _Holder:
     pass
 
@@ -413,7 +442,8 @@ def test_resample_blocks(cuda_dev, built_lib, impl, kind):
 
 
 @pytest.mark.parametrize("impl", [1, 0], ids=["cudacore", "tcgen05"])
-@pytest.mark.parametrize("B,H,C", [(2, 16, 128), (2, 16, 64), (8, 8, 128), (8, 4, 512), (1, 32, 128)])
+@pytest.mark.parametrize("B,H,C", [(2, 16, 128), (2, 16, 64), (8, 8, 128), (8, 4, 512), (1, 32, 128), (3, 32, 64),
+                                   (2, 8, 384), (5, 32, 128)])
 def test_attention_block(cuda_dev, built_lib, impl, B, H, C):
     """AttnBlock (Model.py:145-164): tensor-core batched GEMM path for >= 128 tokens,
     one-kernel path for small maps."""
@@ -470,6 +500,18 @@ def test_time_embed_and_linear(cuda_dev, built_lib):
                                     _lib.stream_ptr()))
     r = F.linear(F.silu(out), W, b)
     assert (y - F.silu(r)).abs().max().item() < 1e-4
+    # row-blocked variant (more than one row): same per-element summation order as the one-row kernel
+    for rows_n in (3, 21):
+        xr = torch.randn(rows_n, ch, device=cuda_dev)
+        yr = torch.empty(rows_n, 512, device=cuda_dev)
+        _lib.check(built_lib.its_linear(yr.data_ptr(), xr.data_ptr(), W.data_ptr(), b.data_ptr(), rows_n, ch, 512, 1, 0, 0,
+                                        _lib.stream_ptr()))
+        y1 = torch.empty(1, 512, device=cuda_dev)
+        for i in (0, rows_n - 1):
+            _lib.check(built_lib.its_linear(y1.data_ptr(), xr[i:i + 1].contiguous().data_ptr(), W.data_ptr(), b.data_ptr(),
+                                            1, ch, 512, 1, 0, 0, _lib.stream_ptr()))
+            assert torch.equal(y1[0], yr[i])
+        assert (yr - F.linear(F.silu(xr), W, b)).abs().max().item() < 1e-4
     table = torch.randn(11, ch, device=cuda_dev)
     idx = torch.tensor([0, 10, 3, 3, 7], dtype=torch.int64, device=cuda_dev)
     rows = torch.empty(B, ch, device=cuda_dev)
