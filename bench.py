@@ -41,6 +41,20 @@ METRIC = "candidate images/sec (T=1000 NFE, verifier incl.)"
 UNIT = "images/s"
 CFG_A = dict(T=1000, ch=128, ch_mult=[1, 2, 3, 4], attn=[1], num_res_blocks=2, dropout=0.15)
 BETA_1, BETA_T = 1e-4, 0.02
+# The default workload is BASELINE.json configs[1] (the configuration the metric is quoted on).  C and E
+# are the other single-GPU shards of BASELINE.json (configs[2]: 256 guided candidates over 8 GPUs = 32 per
+# GPU; configs[4]: 1024 candidates of the 64x64 net over 8 GPUs = 128 per GPU), run by hand / scripts.
+WORKLOADS = {
+    "A": dict(name="random_search_N64_uncond_cifar10_T1000 (BASELINE.json configs[1])", cond=False, img=32, T=1000,
+              attn=[1], candidates=64, w=0.0,
+              unet="Model.UNet ch=128 ch_mult=[1,2,3,4] attn=[1] num_res_blocks=2, random init"),
+    "C": dict(name="random_search_cfg_w1.8_cond_cifar10_T1000 (BASELINE.json configs[2], 32 candidates per GPU)",
+              cond=True, img=32, T=1000, attn=None, candidates=32, w=1.8,
+              unet="ModelCondition.UNet num_labels=10 ch=128 ch_mult=[1,2,3,4] num_res_blocks=2, random init"),
+    "E": dict(name="random_search_uncond_imagenet64_T2000 (BASELINE.json configs[4], 128 candidates per GPU)",
+              cond=False, img=64, T=2000, attn=[2], candidates=128, w=0.0,
+              unet="Model.UNet ch=128 ch_mult=[1,2,3,4] attn=[2] num_res_blocks=2 on 3x64x64, random init"),
+}
 
 
 def peaks():
@@ -155,12 +169,16 @@ def run_reference(args):
 
 
 def workload_config(args, world):
-    return {"workload": "random_search_N64_uncond_cifar10_T1000 (BASELINE.json configs[1])",
-            "unet": "Model.UNet ch=128 ch_mult=[1,2,3,4] attn=[1] num_res_blocks=2, random init",
-            "candidates_per_gpu": args.candidates, "noise_shape": [1, 3, 32, 32], "T": CFG_A["T"],
-            "verifier": "OracleVerifier", "selection": "argmax_first", "global_candidates": args.candidates * world,
-            "parallelism": f"candidate-sharded x{world}",
-            "l2": "per-step working set (163 MB bf16 weights + >1 GB activations per UNet pass) exceeds the 126 MB L2"}
+    wl = WORKLOADS[args.workload]
+    cfg = {"workload": wl["name"], "unet": wl["unet"],
+           "candidates_per_gpu": args.candidates, "noise_shape": [1, 3, wl["img"], wl["img"]], "T": wl["T"],
+           "verifier": "OracleVerifier", "selection": "argmax_first", "global_candidates": args.candidates * world,
+           "parallelism": f"candidate-sharded x{world}",
+           "l2": "per-step working set (163 MB bf16 weights + >1 GB activations per UNet pass) exceeds the 126 MB L2"}
+    if wl["cond"]:
+        cfg["guidance_w"] = wl["w"]
+        cfg["unet_evals_per_step"] = "2 (conditional + unconditional, one 2B-image pass)"
+    return cfg
 
 
 # ------------------------------------------------------------------ GPU arm --
@@ -181,17 +199,26 @@ def run_ours(args):
             ge.build()
         if world > 1:
             dist.barrier()
-    from its_b200.Diffusion import GaussianDiffusionSampler, UNet
     from its_b200.search import search_algorithm as S
     from its_b200.search import verifier as V
 
+    wl = WORKLOADS[args.workload]
+    T, img = wl["T"], wl["img"]
     torch.manual_seed(0)
-    net = UNet(**CFG_A).to(dev).eval()
-    smp = GaussianDiffusionSampler(net, BETA_1, BETA_T, CFG_A["T"]).to(dev)
+    labels = None
+    if wl["cond"]:
+        from its_b200.DiffusionFreeGuidence import GaussianDiffusionSampler, UNet
+        net = UNet(T=T, num_labels=10, ch=128, ch_mult=[1, 2, 3, 4], num_res_blocks=2, dropout=0.15).to(dev).eval()
+        smp = GaussianDiffusionSampler(net, BETA_1, BETA_T, T, w=wl["w"]).to(dev)
+        labels = torch.tensor([3], dtype=torch.int64, device=dev)     # one class per search (noise_shape batch = 1)
+    else:
+        from its_b200.Diffusion import GaussianDiffusionSampler, UNet
+        net = UNet(**dict(CFG_A, T=T, attn=wl["attn"])).to(dev).eval()
+        smp = GaussianDiffusionSampler(net, BETA_1, BETA_T, T).to(dev)
     smp.print_steps = False
     n_local, n_total = args.candidates, args.candidates * world
-    shape = (1, 3, 32, 32)
-    den = S.make_denoise_fn(smp, max_images=args.candidates, seed=1234)
+    shape = (1, 3, img, img)
+    den = S.make_denoise_fn(smp, labels, max_images=args.candidates, seed=1234)
     ver = V.OracleVerifier()
     rs = S.RandomSearch(n_candidates=n_total)
 
@@ -221,7 +248,7 @@ def run_ours(args):
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_per_step = ms.item() / args.steps
     value = n_total / (ms_per_step / 1e3)
-    launches_per_traj = smp.last_launches_per_step * CFG_A["T"]
+    launches_per_traj = smp.last_launches_per_step * T
     gpu_launches = args.steps * (launches_per_traj + 4)   # + image_stats, candidate_scores, argmax, (philox)
 
     # ---- e2e: public API, candidates in pinned host memory, results read back ----
@@ -248,20 +275,23 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
     e2e_value = n_total * args.steps / dt.item()
-    h2d = n_local * 3 * 32 * 32 * 4
+    h2d = n_local * 3 * img * img * 4
     d2h = n_total * 4 + 8
 
     # ---- roofline of the dominant kernel family: every tap-GEMM launch timed with events ----
     pk = peaks()
-    plan = net.plan(n_local, 32, 32, n_img_in=n_local, uniform_t=True)
+    n_net = 2 * n_local if wl["cond"] else n_local
+    plan = net.plan(n_net, img, img, n_img_in=n_local, uniform_t=True)
     roof = profile_tapgemm(plan, dev, pk)
-    roof["step_share"] = roof.pop("sum_ms") * CFG_A["T"] / ms_per_step if ms_per_step else None
-    roof["model_flops_frac_of_sustained"] = (value / world) * plan.flops / n_local * CFG_A["T"] / (pk["sustained"] * 1e12)
+    roof["step_share"] = roof.pop("sum_ms") * T / ms_per_step if ms_per_step else None
+    roof["model_flops_frac_of_sustained"] = (value / world) * plan.flops / n_local * T / (pk["sustained"] * 1e12)
+    if args.workload == "A" and n_local == 64:
+        roof.update(ncu_traffic("tapgemm"))
 
     line = None
     if rank == 0:
         cpu = None
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and args.workload == "A":
             cores = torch.get_num_threads()
             dt_cpu, v_cpu = cpu_reference_sample(8, args.ref_steps)
             cpu = {"value": v_cpu, "unit": UNIT, "cores": cores, "kind": "port",
@@ -279,6 +309,19 @@ def run_ours(args):
         dist.barrier()
         dist.destroy_process_group()
     return line
+
+
+def ncu_traffic(family):
+    """DRAM bytes (read + write) of one UNet pass of this kernel family, from the committed ncu capture of
+    this workload (profiles/r01_traffic_configA_b64.json, written by scripts/summarize_launches.py)."""
+    path = os.path.join(ROOT, "profiles", "r01_traffic_configA_b64.json")
+    try:
+        rec = json.load(open(path))
+        fam = rec["families"][family]
+        return {"traffic": fam["dram_bytes"], "traffic_unit": "bytes per UNet pass, all launches of the family (ncu dram__bytes_read.sum + dram__bytes_write.sum)",
+                "traffic_source": os.path.relpath(path, ROOT)}
+    except (OSError, KeyError, ValueError):
+        return {"traffic": None}
 
 
 def profile_tapgemm(plan, dev, pk):
@@ -321,10 +364,13 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--candidates", type=int, default=64, help="candidates per GPU (weak scaling)")
-    ap.add_argument("--ref-steps", type=int, default=20, help="denoising steps per CPU sample (of T=1000)")
+    ap.add_argument("--workload", default="A", choices=sorted(WORKLOADS), help="A = BASELINE.json configs[1] (default)")
+    ap.add_argument("--candidates", type=int, default=None, help="candidates per GPU (weak scaling); default per workload")
+    ap.add_argument("--ref-steps", type=int, default=100, help="denoising steps per CPU sample (of T=1000)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    if args.candidates is None:
+        args.candidates = WORKLOADS[args.workload]["candidates"]
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -87,7 +87,10 @@ class SamplerBase(nn.Module):
 
     def _sample(self, x_T: torch.Tensor, labels: Optional[torch.Tensor], *, noise=None, seed=None,
                 cand_id0: int = 0, t_start: Optional[int] = None, clip: bool = True,
-                check_nan: bool = True) -> torch.Tensor:
+                check_nan: bool = True, t_stop: int = 0) -> torch.Tensor:
+        """Steps time_step = t_start (default T-1) ... t_stop (default 0) of the ancestral loop on the
+        device; returns x_{t_stop - 1} (x_0, clipped when `clip`, if t_stop == 0).  Per-step noise is
+        keyed by (seed, candidate, time_step), so a trajectory cut into segments equals the uncut one."""
         _lib.require_cuda()
         L = _lib.lib()
         if x_T.device.type != "cuda":
@@ -103,6 +106,9 @@ class SamplerBase(nn.Module):
         first = self.T - 1 if t_start is None else int(t_start)
         if not (0 <= first < self.T):
             raise ValueError(f"t_start={t_start} outside [0, {self.T})")
+        t_stop = int(t_stop)
+        if not (0 <= t_stop <= first):
+            raise ValueError(f"t_stop={t_stop} outside [0, t_start={first}]")
         key = (id(plan), noise is not None, clip, tuple(noise.shape) if noise is not None else None)
         tr = self._traj.get(key)
         if tr is None:
@@ -139,7 +145,7 @@ class SamplerBase(nn.Module):
             _lib.check(L.its_step_advance(plan.t_dev.data_ptr(), -1, s), "its_step_advance")
 
         t_cur = first
-        graph_ok = self.use_cuda_graph and first >= 2
+        graph_ok = self.use_cuda_graph and first - t_stop >= 2
         if graph_ok and (tr.graph is None or tr.seed_args != (seed, cand_id0, w)):
             # (re)capture: seed / candidate base / guidance weight are baked into the graph.
             # One eager step first: it is a real step and it performs the lazy one-time
@@ -152,7 +158,7 @@ class SamplerBase(nn.Module):
             with torch.cuda.graph(g):
                 step()
             tr.graph, tr.seed_args = g, (seed, cand_id0, w)
-        while t_cur >= 0:
+        while t_cur >= t_stop:
             if self.print_steps:
                 print(t_cur)
             if graph_ok:

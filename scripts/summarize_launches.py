@@ -1,6 +1,8 @@
 """Summarise an `ncu --metrics ... --csv` launch list: one row per launch (joined with the op list of
 scripts/profile_pass.py --list when given) and totals per kernel.
-Usage: python scripts/summarize_launches.py launches.csv [kinds.txt]"""
+Usage: python scripts/summarize_launches.py launches.csv [kinds.txt [traffic.json]]
+With a third argument the per-family DRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum) of one UNet
+pass is written as JSON: bench.py reports it as `roofline.traffic`."""
 import collections
 import csv
 import re
@@ -28,7 +30,7 @@ tot = collections.defaultdict(lambda: [0, 0.0, 0.0, 0.0])
 
 
 def short(k):
-    m = re.search(r'tapgemm_persist_kernel<(\d+), (\d+), (\d+), (\d+)>', k)
+    m = re.search(r'tapgemm_persist_kernel<(\d+), (\d+), (\d+), (\d+)', k)
     if m:
         return f"tapgemm_persist<bn{m.group(1)},st{m.group(2)},mt{m.group(3)},ks{m.group(4)}>"
     m = re.search(r'tapgemm_sm100_kernel<(\d+)', k)
@@ -55,3 +57,15 @@ print("kernel                                         n   total_us  avg_us  time
 for k, (n, t, tp, dr) in sorted(tot.items(), key=lambda kv: -kv[1][1]):
     print(f"{k:44s} {n:4d} {t:9.1f} {t/n:7.1f} {tp/t if t else 0:10.1f} {dr:10.1f}")
 print("sum us", round(sum(v[1] for v in tot.values()), 1), "launches", len(launch))
+
+if len(sys.argv) > 3:
+    import json
+    fam = collections.defaultdict(lambda: {"launches": 0, "time_us_under_ncu": 0.0, "dram_bytes": 0.0})
+    for k, (n, t, tp, dr) in tot.items():
+        f = "tapgemm" if k.startswith("tapgemm") else k
+        fam[f]["launches"] += n
+        fam[f]["time_us_under_ncu"] += t
+        fam[f]["dram_bytes"] += dr * 1e6
+    json.dump({"source": path, "note": "one UNet pass; ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,"
+               "gpu__time_duration.sum --clock-control none (cold-cache, serialised launches)", "families": fam},
+              open(sys.argv[3], "w"), indent=1)
