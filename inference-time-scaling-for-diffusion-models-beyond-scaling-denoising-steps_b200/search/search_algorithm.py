@@ -394,36 +394,12 @@ class PathSearch:
 
 
 def _run_prefix(denoise: SamplerDenoiser, x_T: torch.Tensor, stop_step: int, labels) -> torch.Tensor:
-    """x_{stop_step-1 .. }: run the pivot from T-1 down to `stop_step` inclusive and
-    return the un-clipped state that step `stop_step - 1` starts from."""
+    """Run the pivot trajectory from T-1 down to `stop_step` inclusive as one device-resident segment
+    of the sampler's step graph and return the un-clipped state that step `stop_step - 1` starts from."""
     smp = denoise.sampler
     seed = denoise.seed if denoise.seed is not None else 0
-    saved_T = smp.T
-    # Run steps T-1 .. stop_step by driving the public seam; the fused path only knows
-    # "from t_start down to 0", so the prefix uses p_mean_variance + the DDPM step kernel.
-    x = x_T.clone()
-    L = _lib.lib()
-    coef = smp._coef_table(x.device)
-    B = x.shape[0]
-    n_per = x[0].numel()
-    t_dev = torch.zeros(1, dtype=torch.int32, device=x.device)
-    nan_flag = torch.zeros(1, dtype=torch.int32, device=x.device)
-    guided = getattr(smp, "guided", False)
-    net = smp._unet()
-    lab = None
-    if guided:
-        lab = (labels if labels is not None else denoise.labels).reshape(-1).to(x.device, torch.int64)
-    for step in range(saved_T - 1, stop_step - 1, -1):
-        t = torch.full((B,), step, dtype=torch.int64, device=x.device)
-        if guided:
-            both = net(torch.cat([x, x]), torch.cat([t, t]), torch.cat([lab, torch.zeros_like(lab)]))
-            e_c, e_u = both[:B].contiguous(), both[B:].contiguous()
-        else:
-            e_c, e_u = net(x, t), None
-        t_dev.fill_(step)
-        _lib.check(L.its_ddpm_step(x.data_ptr(), e_c.data_ptr(), None if e_u is None else e_u.data_ptr(), None,
-                                   0, B, n_per, coef.data_ptr(), t_dev.data_ptr(), float(getattr(smp, "w", 0.0)),
-                                   seed, 0, nan_flag.data_ptr(), 0, _lib.stream_ptr()), "its_ddpm_step")
-    if int(nan_flag.item()) != 0:
-        raise AssertionError("nan in tensor.")
-    return x
+    kw = dict(seed=seed, cand_id0=0, t_stop=stop_step, clip=False)
+    if getattr(smp, "guided", False):
+        lab = (labels if labels is not None else denoise.labels).reshape(-1).to(x_T.device, torch.int64)
+        return smp(x_T, lab, **kw)
+    return smp(x_T, **kw)

@@ -6,6 +6,7 @@ Tolerances (north_star): samples within max-abs 2e-2 in bf16; verifier scores
 within 1e-3; selected candidate index exact whenever the top-2 margin exceeds
 the score tolerance."""
 import math
+import os
 
 import numpy as np
 import pytest
@@ -249,3 +250,37 @@ def test_random_search_philox_population(cuda_dev):
     ps = S.PathSearch(n_paths=3, injection_step=cfg["T"] // 2, noise_scale=0.1)
     pn, pscore, ph = ps.search(n1, den, ver.score, timesteps=cfg["T"], device="cuda", seed=7, restart=True)
     assert len(ph["scores"]) == 3 and math.isfinite(pscore)
+
+
+def test_path_search_restart_continues_the_pivot_trajectory(cuda_dev):
+    """restart=True with zero perturbation: path 0 (global candidate 0) is the pivot's own trajectory cut
+    at injection_step and resumed, so its score equals the uncut trajectory's, bit for bit."""
+    cfg = cases.SEARCH_CASES["u_search"]
+    S, den, ver = _search_setup(cfg, cuda_dev)
+    den.step_noise = None
+    den.seed = 9
+    shape = tuple(cfg["noise_shape"])
+    x_T = S.philox_normal((1,) + shape, 3, 0, S.TAG_X_T, cuda_dev)[0]
+    ps = S.PathSearch(n_paths=2, injection_step=cfg["T"] // 2, noise_scale=0.1)
+    zeros = torch.zeros((2,) + shape, device=cuda_dev)
+    pn, pscore, ph = ps.search(x_T, den, ver.score, timesteps=cfg["T"], device="cuda", variations=zeros, restart=True)
+    whole = den.sampler(x_T, seed=9, cand_id0=0)
+    assert ph["scores"][0] == ver.score(whole)
+    assert ph["injection_points"] == [cfg["T"] // 2] * 2
+
+
+def test_multi_gpu_searches_agree_with_single_rank(cuda_dev):
+    """torchrun x2 over NCCL: random / zero-order / path searches select the same candidate on every
+    rank, bit-identical to one rank evaluating the whole population (scripts/search_multi_gpu.py)."""
+    import json
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29517",
+                        os.path.join(root, "scripts", "search_multi_gpu.py")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    rep = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    assert rep["ok"] and rep["world"] == 2
