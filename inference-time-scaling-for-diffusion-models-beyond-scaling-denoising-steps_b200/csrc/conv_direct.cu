@@ -75,46 +75,56 @@ __global__ void __launch_bounds__(256) conv_head_kernel(
 // to be multiplied with the packed weights [w_hi | w_hi | w_lo | 0] by a 1x1 tap-GEMM: the three
 // products x_hi*w_hi + x_lo*w_hi + x_hi*w_lo keep ~16 mantissa bits of the fp32 convolution
 // (Model.py:269 runs it in fp32; x_t reaches +-30 at early steps).
-__global__ void __launch_bounds__(256) head_patches_kernel(__nv_bfloat16* __restrict__ out,
-                                                           const float* __restrict__ x, long long nvec,
-                                                           int n_img_in, int H, int Wd, int Cin) {
+// One thread gathers the 9*Cin values of one pixel's patch (zero outside the image), splits them
+// into hi / lo and writes the 256-byte patch row into a per-warp staging tile; the warp then streams
+// its 32 consecutive patch rows (8 KB, contiguous in global memory) out with coalesced 16-byte stores.
+constexpr int HP_THREADS = 128;
+template <int Cin>
+__global__ void __launch_bounds__(HP_THREADS) head_patches_kernel(__nv_bfloat16* __restrict__ out,
+                                                                  const float* __restrict__ x, long long npix,
+                                                                  int n_img_in, int H, int Wd) {
+  __shared__ uint4 s_tile[HP_THREADS / 32][32][17];      // pitch 17: conflict-free both ways
   pdl_prologue();
-  // per patch channel k: which term (0 hi, 1 lo, 2 hi, 3 zero) and which tap (ci, dy, dx); the
-  // table replaces ~10 integer divisions per element
-  __shared__ int8_t s_term[128], s_ci[128], s_dy[128], s_dx[128];
-  const int K = Cin * 9;
-  if (threadIdx.x < 128) {
-    const int k = threadIdx.x;
-    const int term = k / K, t = k - term * K;
-    const int ci = t / 9, r = t - ci * 9, ky = r / 3, kx = r - ky * 3;
-    s_term[k] = (int8_t)(term < 3 ? term : 3);
-    s_ci[k] = (int8_t)ci; s_dy[k] = (int8_t)(ky - 1); s_dx[k] = (int8_t)(kx - 1);
-  }
-  __syncthreads();
+  constexpr int K = Cin * 9;                             // 3K <= 128
   const int HW = H * Wd;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int v = (int)(i & 15);
-    const long long pix = i >> 4;
-    const int b = (int)(pix / HW);
-    const int rem = (int)(pix - (long long)b * HW);
-    const int y = rem / Wd, xw = rem - y * Wd;
-    const float* xin = x + (long long)(b % n_img_in) * Cin * HW;
-    float f[8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (long long base = (blockIdx.x * (long long)(HP_THREADS / 32) + warp) * 32; base < npix;
+       base += (long long)gridDim.x * HP_THREADS) {
+    const long long pix = base + lane;
+    __nv_bfloat16 row[128];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int k = v * 8 + j;
-      const int term = s_term[k];
-      const int yy = y + s_dy[k], xx = xw + s_dx[k];
-      float val = 0.f;
-      if (term < 3 && yy >= 0 && yy < H && xx >= 0 && xx < Wd) {
-        const float xv = __ldg(xin + s_ci[k] * HW + yy * Wd + xx);
-        const float hi = __bfloat162float(__float2bfloat16_rn(xv));
-        val = (term == 1) ? xv - hi : hi;
+    for (int k = 0; k < 128; ++k) row[k] = __float2bfloat16_rn(0.f);
+    if (pix < npix) {
+      const int b = (int)(pix / HW);
+      const int rem = (int)(pix - (long long)b * HW);
+      const int y = rem / Wd, xw = rem - y * Wd;
+      const float* xin = x + (long long)(b % n_img_in) * Cin * HW;
+#pragma unroll
+      for (int t = 0; t < K; ++t) {
+        {
+          const int ci = t / 9, r = t - ci * 9, ky = r / 3, kx = r - ky * 3;
+          const int yy = y + ky - 1, xx = xw + kx - 1;
+          float xv = 0.f;
+          if (yy >= 0 && yy < H && xx >= 0 && xx < Wd) xv = __ldg(xin + ci * HW + yy * Wd + xx);
+          const __nv_bfloat16 hi = __float2bfloat16_rn(xv);
+          const __nv_bfloat16 lo = __float2bfloat16_rn(xv - __bfloat162float(hi));
+          row[t] = hi;
+          if (K + t < 128) row[K + t] = lo;
+          if (2 * K + t < 128) row[2 * K + t] = hi;
+        }
       }
-      f[j] = val;
     }
-    *reinterpret_cast<bf16x8*>(out + i * 8) = pack8(f);
+#pragma unroll
+    for (int v = 0; v < 16; ++v) s_tile[warp][lane][v] = *reinterpret_cast<const uint4*>(&row[v * 8]);
+    __syncwarp();
+    // 32 rows x 16 vectors = 512 consecutive 16-byte words of global memory
+    uint4* dst = reinterpret_cast<uint4*>(out) + base * 16;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int w = j * 32 + lane;
+      if (base + (w >> 4) < npix) dst[w] = s_tile[warp][w >> 4][w & 15];
+    }
+    __syncwarp();
   }
 }
 
@@ -341,11 +351,19 @@ extern "C" int its_head_patches(void* out, const float* x, int32_t n_img, int32_
   ITS_REQUIRE(out && x, "its_head_patches: null pointer");
   ITS_REQUIRE(n_img > 0 && n_img_in > 0 && H > 0 && Wd > 0 && Cin >= 1 && Cin * 27 <= 128,
               "its_head_patches: unsupported shape Cin=%d (3 * 9 * Cin must fit 128 patch channels)", Cin);
-  const long long nvec = (long long)n_img * H * Wd * 16;
-  long long blocks = (nvec + 255) / 256;
-  if (blocks > 148 * 8) blocks = 148 * 8;
-  ITS_LAUNCH(head_patches_kernel, dim3((unsigned)blocks), dim3(256), 0, as_stream(stream),
-             static_cast<__nv_bfloat16*>(out), x, nvec, n_img_in, H, Wd, Cin);
+  const long long npix = (long long)n_img * H * Wd;
+  long long blocks = (npix + HP_THREADS - 1) / HP_THREADS;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+#define ITS_HP_CASE(CIN_)                                                                              \
+  case CIN_:                                                                                         \
+    ITS_LAUNCH(head_patches_kernel<CIN_>, dim3((unsigned)blocks), dim3(HP_THREADS), 0, as_stream(stream), \
+               static_cast<__nv_bfloat16*>(out), x, npix, n_img_in, H, Wd);                          \
+    break;
+  switch (Cin) {
+    ITS_HP_CASE(1) ITS_HP_CASE(2) ITS_HP_CASE(3) ITS_HP_CASE(4)
+    default: return set_error(ITS_ERR_INVALID, "its_head_patches: Cin=%d", Cin);
+  }
+#undef ITS_HP_CASE
   return ITS_OK;
 }
 
