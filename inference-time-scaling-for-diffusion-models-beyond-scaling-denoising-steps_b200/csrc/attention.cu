@@ -26,6 +26,57 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(__nv_bfloat16* __rest
   for (int c = lane; c < n_cols; c += 32) p[c] = __float2bfloat16_rn(__expf(s[c] - m) * inv);
 }
 
+// One CTA per (image, query token): for very small maps (N <= 32 tokens) one CTA per image cannot
+// keep its warps busy (4 queries per warp pass), so the queries are spread over the grid instead.  qkv [n_img][N][3C] bf16, out [n_img][N][C].
+__global__ void __launch_bounds__(256) attention_tiny_kernel(__nv_bfloat16* __restrict__ out,
+                                                              const __nv_bfloat16* __restrict__ qkv,
+                                                              int N, int C, float scale) {
+  pdl_prologue();
+  __shared__ float s_p[64];
+  const int img = blockIdx.y, qi = blockIdx.x;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const __nv_bfloat16* base = qkv + (long long)img * N * 3 * C;
+  const __nv_bfloat16* q = base + (long long)qi * 3 * C;
+  const int nv = C / 8;
+  for (int j = warp; j < N; j += 8) {
+    const __nv_bfloat16* k = base + (long long)j * 3 * C + C;
+    float acc = 0.f;
+    for (int v = lane; v < nv; v += 32) {
+      float fq[8], fk[8];
+      unpack8(*reinterpret_cast<const bf16x8*>(q + v * 8), fq);
+      unpack8(*reinterpret_cast<const bf16x8*>(k + v * 8), fk);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc = fmaf(fq[i], fk[i], acc);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) s_p[j] = acc * scale;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    float m = -INFINITY;
+    for (int j = lane; j < N; j += 32) m = fmaxf(m, s_p[j]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    float sum = 0.f;
+    for (int j = lane; j < N; j += 32) sum += __expf(s_p[j] - m);
+    sum = warp_sum(sum);
+    const float inv = 1.0f / sum;
+    for (int j = lane; j < N; j += 32) s_p[j] = __expf(s_p[j] - m) * inv;
+  }
+  __syncthreads();
+  for (int c2 = tid; c2 < C / 2; c2 += blockDim.x) {
+    float a0 = 0.f, a1 = 0.f;
+    for (int j = 0; j < N; ++j) {
+      const float2 vv = __bfloat1622float2(
+          *reinterpret_cast<const __nv_bfloat162*>(base + (long long)j * 3 * C + 2 * C + 2 * c2));
+      a0 = fmaf(s_p[j], vv.x, a0);
+      a1 = fmaf(s_p[j], vv.y, a1);
+    }
+    *reinterpret_cast<__nv_bfloat162*>(out + ((long long)img * N + qi) * C + 2 * c2) =
+        __floats2bfloat162_rn(a0, a1);
+  }
+}
+
 // One CTA per image: q, k, v rows staged once in shared memory (row pitch C + 8 halfwords, so the
 // 16-byte reads of 32 different key rows hit 32 different bank groups), then each warp takes QB
 // queries at a time: scores with lane = key (N <= 64: two keys per lane), softmax across the warp,
@@ -129,6 +180,13 @@ extern "C" int its_attention_small(void* out, const void* qkv, int32_t n_img, in
   ITS_REQUIRE(out && qkv, "its_attention_small: null pointer");
   ITS_REQUIRE(n_img > 0 && n_img <= 65535 && N > 0 && N <= 64 && C > 0 && C % 8 == 0,
               "its_attention_small: unsupported N=%d C=%d n_img=%d", N, C, n_img);
+  if (N <= 32) {
+    ITS_REQUIRE(n_img <= 65535, "its_attention_small: n_img");
+    ITS_LAUNCH(its::attention_tiny_kernel, dim3(N, n_img), dim3(256), 0, its::as_stream(stream),
+               static_cast<__nv_bfloat16*>(out), static_cast<const __nv_bfloat16*>(qkv), N, C, scale);
+    ITS_CHECK_LAUNCH();
+    return ITS_OK;
+  }
   const size_t smem = (size_t)3 * N * (C + 8) * 2 + 8 * its::AS_QB * 64 * 4;
   ITS_REQUIRE(smem <= 227 * 1024, "its_attention_small: N=%d C=%d needs %zu bytes of shared memory", N, C, smem);
   static size_t configured = 0;

@@ -47,6 +47,7 @@ struct FlashParams {
   const float* bias_v;
   int N;
   float scale_log2e;
+  int v_mn;      // 1: V blocks come MN-major from the fused q|k|v tensor (boxes of 64 channels x 128 keys)
 };
 
 template <int C>
@@ -138,8 +139,13 @@ attention_flash_kernel(const FlashParams p, const __grid_constant__ CUtensorMap 
         if (elect_one_sync()) {
           uint8_t* dst = ring + stage * L::STAGE_BYTES;
           mbar_expect_tx(&full_bar[stage], (uint32_t)L::STAGE_BYTES);
-          for (int kp = 0; kp < 2; ++kp)
-            tma_load_3d(dst + kp * C * 128, &tmV, &full_bar[stage], (j - 1) * FL_KB + kp * 64, 0, img);
+          if (p.v_mn) {
+            for (int cp = 0; cp < NKC; ++cp)
+              tma_load_3d(dst + cp * 16384, &tmV, &full_bar[stage], 2 * C + cp * 64, (j - 1) * FL_KB, img);
+          } else {
+            for (int kp = 0; kp < 2; ++kp)
+              tma_load_3d(dst + kp * C * 128, &tmV, &full_bar[stage], (j - 1) * FL_KB + kp * 64, 0, img);
+          }
         }
         __syncwarp();
         ++it;
@@ -187,10 +193,19 @@ attention_flash_kernel(const FlashParams p, const __grid_constant__ CUtensorMap 
 #pragma unroll
           for (int kp = 0; kp < 2; ++kp) {
             const uint64_t adesc = make_smem_desc(smem_u32(p_smem + b * L::P_BYTES + kp * 16384));
-            const uint64_t bdesc = make_smem_desc(v_addr + kp * C * 128);
+            if (p.v_mn) {
+              // B = V[128 keys][C channels], MN-major: channel panels 16 KB apart, 16 keys = 2 KB further on
+              const uint64_t bdesc = make_smem_desc_mn(v_addr, 16384);
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_bf16(tmem_base + 256 + b * 128, adesc + 2 * k, bdesc + 2 * k, idesc_t, (uint32_t)((kp | k) != 0));
+              for (int k = 0; k < 4; ++k)
+                umma_bf16(tmem_base + 256 + b * 128, adesc + 2 * k, bdesc + 128 * (kp * 4 + k),
+                          idesc_t | IDESC_B_MN_MAJOR, (uint32_t)((kp | k) != 0));
+            } else {
+              const uint64_t bdesc = make_smem_desc(v_addr + kp * C * 128);
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_bf16(tmem_base + 256 + b * 128, adesc + 2 * k, bdesc + 2 * k, idesc_t, (uint32_t)((kp | k) != 0));
+            }
           }
           umma_commit(&empty_bar[stage]);
           umma_commit(&p_free[b]);
@@ -350,7 +365,9 @@ static int launch_flash(const FlashParams& p, const CUtensorMap& tmQ, const CUte
 extern "C" int its_attention_flash(void* out, const void* qk, const void* vT, const float* bias_v,
                                    int32_t n_img, int32_t N, int32_t C, float scale, void* stream) {
   using namespace its;
-  ITS_REQUIRE(out && qk && vT, "its_attention_flash: null pointer");
+  ITS_REQUIRE(out && qk, "its_attention_flash: null pointer");
+  const bool v_mn = (vT == nullptr);     // qk is the fused q|k|v tensor [n_img][N][3C]
+  const int pitch = v_mn ? 3 * C : 2 * C;
   ITS_REQUIRE(N % FL_KB == 0 && N >= 2 * FL_KB, "its_attention_flash: N=%d tokens must be a multiple of %d, at least %d", N,
               FL_KB, 2 * FL_KB);
   ITS_REQUIRE(C == 64 || C == 128, "its_attention_flash: C=%d (64 or 128 supported; use the GEMM + softmax path)", C);
@@ -360,15 +377,21 @@ extern "C" int its_attention_flash(void* out, const void* qk, const void* vT, co
   CUtensorMap tmQ, tmK, tmV, tmO;
   const cuuint32_t estr[3] = {1, 1, 1};
   {
-    const cuuint64_t dims[3] = {(cuuint64_t)2 * C, (cuuint64_t)N, (cuuint64_t)n_img};
-    const cuuint64_t strides[2] = {(cuuint64_t)2 * C * 2, (cuuint64_t)N * 2 * C * 2};
+    const cuuint64_t dims[3] = {(cuuint64_t)pitch, (cuuint64_t)N, (cuuint64_t)n_img};
+    const cuuint64_t strides[2] = {(cuuint64_t)pitch * 2, (cuuint64_t)N * pitch * 2};
     const cuuint32_t box[3] = {64, 128, 1};
     int rc = encode_bf16_map(&tmQ, 3, qk, dims, strides, box, estr, "attention Q");
     if (rc != ITS_OK) return rc;
     rc = encode_bf16_map(&tmK, 3, qk, dims, strides, box, estr, "attention K");
     if (rc != ITS_OK) return rc;
   }
-  {
+  if (v_mn) {
+    const cuuint64_t dims[3] = {(cuuint64_t)pitch, (cuuint64_t)N, (cuuint64_t)n_img};
+    const cuuint64_t strides[2] = {(cuuint64_t)pitch * 2, (cuuint64_t)N * pitch * 2};
+    const cuuint32_t box[3] = {64, 128, 1};
+    int rc = encode_bf16_map(&tmV, 3, qk, dims, strides, box, estr, "attention V");
+    if (rc != ITS_OK) return rc;
+  } else {
     const cuuint64_t dims[3] = {(cuuint64_t)N, (cuuint64_t)C, (cuuint64_t)n_img};
     const cuuint64_t strides[2] = {(cuuint64_t)N * 2, (cuuint64_t)C * N * 2};
     const cuuint32_t box[3] = {64, (cuuint32_t)C, 1};
@@ -386,6 +409,7 @@ extern "C" int its_attention_flash(void* out, const void* qk, const void* vT, co
   p.bias_v = bias_v;
   p.N = N;
   p.scale_log2e = scale * 1.4426950408889634f;
+  p.v_mn = v_mn ? 1 : 0;
   if (C == 64) return launch_flash<64>(p, tmQ, tmK, tmV, tmO, n_img, as_stream(stream));
   return launch_flash<128>(p, tmQ, tmK, tmV, tmO, n_img, as_stream(stream));
 }

@@ -33,6 +33,7 @@ struct AttnParams {
   const float* bias_v;   // [C] or null
   int C;                 // channels (head dim), multiple of 64, <= 384
   float scale_log2e;     // C^-0.5 * log2(e)
+  int v_mn;              // 1: V comes MN-major from the fused q|k|v tensor (tmV boxes of 64 channels x 64 keys)
 };
 
 __global__ void __launch_bounds__(AT_THREADS, 1)
@@ -100,8 +101,13 @@ attention_fused_kernel(const AttnParams p, const __grid_constant__ CUtensorMap t
         } else {
           const int kn = kb - nkc;               // 64 keys x C channels of V^T
           mbar_expect_tx(&full_bar[stage], (uint32_t)(C * 128));
-          for (int h = 0; h < nd; ++h)
-            tma_load_3d(dst + h * dn * 128, &tmV, &full_bar[stage], kn * 64, h * dn, img);
+          if (p.v_mn) {                          // V rows as they are: panels of 64 channels x 64 keys
+            for (int cp = 0; cp < nkc; ++cp)
+              tma_load_3d(dst + cp * 8192, &tmV, &full_bar[stage], 2 * C + cp * 64, kn * 64, img);
+          } else {
+            for (int h = 0; h < nd; ++h)
+              tma_load_3d(dst + h * dn * 128, &tmV, &full_bar[stage], kn * 64, h * dn, img);
+          }
         }
       }
       __syncwarp();
@@ -135,10 +141,19 @@ attention_fused_kernel(const AttnParams p, const __grid_constant__ CUtensorMap t
         const uint64_t adesc = make_smem_desc(smem_u32(p_smem + kn * 16384));
         const uint32_t b_addr = smem_u32(smem + stage * AT_STAGE);
         for (int h = 0; h < nd; ++h) {
-          const uint64_t bdesc = make_smem_desc(b_addr + h * dn * 128);
+          if (p.v_mn) {
+            // B = V[64 keys][dn channels], MN-major: channel panels 8 KB apart, 16 keys = 2 KB further on
+            const uint64_t bdesc = make_smem_desc_mn(b_addr + h * (dn / 64) * 8192, 8192);
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16(tmem_base + h * dn, adesc + 2 * k, bdesc + 2 * k, idesc_o, (uint32_t)((kn | k) != 0));
+            for (int k = 0; k < 4; ++k)
+              umma_bf16(tmem_base + h * dn, adesc + 2 * k, bdesc + 128 * k, idesc_o | IDESC_B_MN_MAJOR,
+                        (uint32_t)((kn | k) != 0));
+          } else {
+            const uint64_t bdesc = make_smem_desc(b_addr + h * dn * 128);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_bf16(tmem_base + h * dn, adesc + 2 * k, bdesc + 2 * k, idesc_o, (uint32_t)((kn | k) != 0));
+          }
         }
         umma_commit(&empty_bar[stage]);
         if (kn == NKN - 1) umma_commit(o_full);
@@ -255,18 +270,21 @@ attention_fused_kernel(const AttnParams p, const __grid_constant__ CUtensorMap t
 extern "C" int its_attention_fused(void* out, const void* qk, const void* vT, const float* bias_v,
                                    int32_t n_img, int32_t N, int32_t C, float scale, void* stream) {
   using namespace its;
-  ITS_REQUIRE(out && qk && vT, "its_attention_fused: null pointer");
+  ITS_REQUIRE(out && qk, "its_attention_fused: null pointer");
+  const bool v_mn = (vT == nullptr);     // qk is the fused q|k|v tensor [n_img][N][3C]
+  const int pitch = v_mn ? 3 * C : 2 * C;
   ITS_REQUIRE(N == AT_N, "its_attention_fused: N=%d tokens (only %d supported; use the GEMM + softmax path)", N, AT_N);
   ITS_REQUIRE(C % 64 == 0 && C >= 64 && C <= 384, "its_attention_fused: C=%d must be a multiple of 64 in [64, 384]", C);
   ITS_REQUIRE(n_img > 0, "its_attention_fused: n_img");
   ITS_REQUIRE(((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(qk) | reinterpret_cast<uintptr_t>(vT)) & 15) == 0,
               "its_attention_fused: pointer alignment");
+  ITS_REQUIRE(!v_mn || C <= 256 || (C / 2) % 64 == 0, "its_attention_fused: C=%d", C);
   static_assert(AT_SMEM <= 227 * 1024, "shared memory budget");
   CUtensorMap tmQ, tmK, tmV, tmO;
   const cuuint32_t estr[3] = {1, 1, 1};
   {
-    const cuuint64_t dims[3] = {(cuuint64_t)2 * C, (cuuint64_t)N, (cuuint64_t)n_img};
-    const cuuint64_t strides[2] = {(cuuint64_t)2 * C * 2, (cuuint64_t)N * 2 * C * 2};
+    const cuuint64_t dims[3] = {(cuuint64_t)pitch, (cuuint64_t)N, (cuuint64_t)n_img};
+    const cuuint64_t strides[2] = {(cuuint64_t)pitch * 2, (cuuint64_t)N * pitch * 2};
     const cuuint32_t boxq[3] = {64, 128, 1};
     const cuuint32_t boxk[3] = {64, (cuuint32_t)AT_N, 1};
     int rc = encode_bf16_map(&tmQ, 3, qk, dims, strides, boxq, estr, "attention Q");
@@ -274,7 +292,13 @@ extern "C" int its_attention_fused(void* out, const void* qk, const void* vT, co
     rc = encode_bf16_map(&tmK, 3, qk, dims, strides, boxk, estr, "attention K");
     if (rc != ITS_OK) return rc;
   }
-  {
+  if (v_mn) {
+    const cuuint64_t dims[3] = {(cuuint64_t)pitch, (cuuint64_t)N, (cuuint64_t)n_img};
+    const cuuint64_t strides[2] = {(cuuint64_t)pitch * 2, (cuuint64_t)N * pitch * 2};
+    const cuuint32_t box[3] = {64, 64, 1};
+    int rc = encode_bf16_map(&tmV, 3, qk, dims, strides, box, estr, "attention V");
+    if (rc != ITS_OK) return rc;
+  } else {
     const int dn = C > 256 ? C / 2 : C;
     const cuuint64_t dims[3] = {(cuuint64_t)N, (cuuint64_t)C, (cuuint64_t)n_img};
     const cuuint64_t strides[2] = {(cuuint64_t)N * 2, (cuuint64_t)C * N * 2};
@@ -293,6 +317,7 @@ extern "C" int its_attention_fused(void* out, const void* qk, const void* vT, co
   p.bias_v = bias_v;
   p.C = C;
   p.scale_log2e = scale * 1.4426950408889634f;
+  p.v_mn = v_mn ? 1 : 0;
   static bool configured = false;
   if (!configured) {
     ITS_CHECK_CUDA(cudaFuncSetAttribute(attention_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));

@@ -132,6 +132,21 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
   d |= (uint64_t)2 << 61;                        // layout type: SWIZZLE_128B
   return d;
 }
+// MN-major, SWIZZLE_128B operand (the MN index runs along the 128-byte rows, K across rows — what a TMA
+// box {64 MN elements, k rows} deposits): canonical layout ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte
+// units, i.e. LBO = byte distance between consecutive 64-element MN panels, SBO = byte distance between
+// consecutive groups of 8 K rows (1024 when the rows of a panel are contiguous).
+__device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t saddr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFFu);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+constexpr uint32_t IDESC_B_MN_MAJOR = 1u << 16;   // instruction descriptor: B operand is MN-major
+
 // Instruction descriptor: D fp32, A and B both bf16 (format 1) or both IEEE fp16 (format 0; mixed
 // formats are an illegal instruction), both K-major, M=128, N=BN.
 __host__ __device__ constexpr uint32_t make_idesc(int bn, bool fp16 = false) {

@@ -94,6 +94,7 @@ class UNetPlan:
         self.stats_of, self.schedule, self.fold_residual = {}, 0, True
         self.ws_persist, self.sm_count, self.fused_attention = None, 148, True
         self.head_on_tensor_cores = True
+        self.attn_v_mn = _os.environ.get("ITS_ATTN_VT", "0") != "1"
         self.gn_dtype = FP16 if (FP16_GN and impl != 1) else BF16
         return self
 
@@ -395,6 +396,22 @@ class UNetPlan:
         one = [(0, 0, 0)]
         tensor_path = N > 64      # batched-GEMM formulation (tcgen05, or its CUDA-core twin when forced)
         if tensor_path:
+            fused256 = N == 256 and Cc % 64 == 0 and Cc <= 384
+            flash = N % 128 == 0 and N > 256 and Cc in (64, 128)
+            if (fused256 or flash) and self._impl_for([Cc], Cc) == 0 and self.fused_attention and self.attn_v_mn:
+                # one projection launch for q|k|v; the attention core reads V as an MN-major B operand
+                # straight from that tensor (no V^T projection launch)
+                wqkv = self._hold(torch.cat([wq, wk, wv], 0), torch.float32)
+                bqk0 = self._hold(torch.cat([bq, bk, torch.zeros_like(bv)], 0), torch.float32)
+                qkv = self.conv([(a, Cc, 0, 1, False)], [(one, 0, 0, 0)], H, W, wqkv, 3 * Cc, bias=bqk0, want_stats=False)
+                o = self._new((B, H, W, Cc))
+                bvh = self._hold(bv, torch.float32)     # added after the product: the rows of softmax(S) sum to one
+                self._op(self.L.its_attention_fused if fused256 else self.L.its_attention_flash, o.data_ptr(),
+                         qkv.data_ptr(), None, bvh.data_ptr(), B, N, Cc, scale, flops=4 * B * N * N * Cc,
+                         kind="attention_fused" if fused256 else "attention_flash")
+                wp = self._hold(at.proj.weight.detach().float()[:, :, 0, 0], torch.float32)
+                bp = self._hold(at.proj.bias, torch.float32)
+                return self.conv([(o, Cc, 0, 1, False)], [(one, 0, 0, 0)], H, W, wp, Cc, bias=bp, res=x)
             wqk = self._hold(torch.cat([wq, wk], 0), torch.float32)
             bqk = self._hold(torch.cat([bq, bk], 0), torch.float32)
             qk = self.conv([(a, Cc, 0, 1, False)], [(one, 0, 0, 0)], H, W, wqk, 2 * Cc, bias=bqk, want_stats=False)
@@ -402,8 +419,6 @@ class UNetPlan:
             wv_img = self._hold(wv.reshape(1, 1, Cc, Cc), a.dtype)
             vT = self.conv([(wv_img, Cc, 0, 1, True)], [(one, 0, 0, 0)], 1, Cc, a.view(B, N, Cc), N,
                            w_batch_stride=N * Cc, out_shape=(B, 1, Cc, N), want_stats=False)
-            fused256 = N == 256 and Cc % 64 == 0 and Cc <= 384
-            flash = N % 128 == 0 and N > 256 and Cc in (64, 128)
             if (fused256 or flash) and self._impl_for([Cc], Cc) == 0 and self.fused_attention:
                 # scores in TMEM, probabilities in shared memory: one launch for QK^T, softmax and PV
                 o = self._new((B, H, W, Cc))
@@ -527,6 +542,7 @@ class UNetPlan:
         self.schedule = int(_os.environ.get("ITS_SCHEDULE", "0"))
         self.fused_attention = _os.environ.get("ITS_FUSED_ATTENTION", "1") != "0"
         self.head_on_tensor_cores = _os.environ.get("ITS_HEAD_TC", "1") != "0"
+        self.attn_v_mn = _os.environ.get("ITS_ATTN_VT", "0") != "1"
         self.gn_dtype = FP16 if (FP16_GN and ch % 64 == 0 and self.impl_forced != 1) else BF16
         self.x_in = self._new((self.n_img_in, 3, H, W), torch.float32)
         self.t_dev = torch.zeros(1, dtype=torch.int32, device=self.dev)

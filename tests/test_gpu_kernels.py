@@ -443,7 +443,7 @@ def test_resample_blocks(cuda_dev, built_lib, impl, kind):
 
 @pytest.mark.parametrize("impl", [1, 0], ids=["cudacore", "tcgen05"])
 @pytest.mark.parametrize("B,H,C", [(2, 16, 128), (2, 16, 64), (8, 8, 128), (8, 4, 512), (1, 32, 128), (3, 32, 64),
-                                   (2, 8, 384), (5, 32, 128)])
+                                   (2, 8, 384), (5, 32, 128), (2, 16, 384), (3, 16, 256)])
 def test_attention_block(cuda_dev, built_lib, impl, B, H, C):
     """AttnBlock (Model.py:145-164): tensor-core batched GEMM path for >= 128 tokens,
     one-kernel path for small maps."""
@@ -468,6 +468,34 @@ def test_attention_block(cuda_dev, built_lib, impl, B, H, C):
             sd[f"a.{nme}.bias"] = getattr(at, nme).bias
         ref = O._attn(sd, "a", bf(x), O._Q(None))
     check_close(nchw(out), ref, 1.5e-2, "attention")
+
+
+@pytest.mark.parametrize("B,H,C", [(2, 16, 128), (2, 16, 384), (2, 32, 128)])
+def test_attention_v_transposed_operand_path_matches_mn_major_path(cuda_dev, built_lib, B, H, C, monkeypatch):
+    """The fused cores read V either MN-major from the q|k|v tensor (default) or K-major from a V^T
+    projection (ITS_ATTN_VT=1): same products, same order -> the block outputs agree to bf16 rounding of
+    one intermediate (V is rounded once either way, the projections are separate launches)."""
+    from its_b200.engine import UNetPlan
+    torch.manual_seed(7)
+    at = _Holder()
+    at.group_norm = torch.nn.GroupNorm(32, C).to(cuda_dev)
+    for nme in ("proj_q", "proj_k", "proj_v", "proj"):
+        setattr(at, nme, torch.nn.Conv2d(C, C, 1).to(cuda_dev))
+    x = torch.randn(B, C, H, H, device=cuda_dev)
+    xin = nhwc(x)
+    outs = []
+    for vt in ("0", "1"):
+        monkeypatch.setenv("ITS_ATTN_VT", vt)
+        plan = UNetPlan.scratch(cuda_dev, B, 0)
+        with torch.no_grad():
+            out = plan._attn_block(at, xin)
+            plan.run()
+        kinds = [k for k, _, _ in plan.op_info]
+        assert ("attention_fused" in kinds) or ("attention_flash" in kinds)
+        assert len(kinds) == (4 if vt == "0" else 5)        # GN, qkv, core, proj (+ V^T projection)
+        outs.append(nchw(out).clone())
+    torch.cuda.synchronize()
+    check_close(outs[0], outs[1], 4e-3, "mn-major vs V^T")
 
 
 def test_softmax_rows(cuda_dev, built_lib):
