@@ -281,6 +281,15 @@ int its_attention_flash(void* out, const void* qk, const void* vT,
                         const float* bias_v, int32_t n_img, int32_t N, int32_t C,
                         float scale, void* stream);
 
+/* Attention core for small maps (N = 16, 32 or 64 tokens: 4x4 / 8x8 maps of
+ * Model.py:153-158, ModelCondition.py:108-113) on the tensor cores: 128 / N
+ * consecutive images share one 128-row tile, the softmax is masked to the keys of
+ * the row's own image.  qkv is the fused projection tensor [n_img][N][3C] (q|k|v,
+ * bf16; the V bias is NOT folded in: it is added after the product, the rows of
+ * softmax(S) sum to one), out is [n_img][N][C].  C a multiple of 64, <= 512.   */
+int its_attention_group(void* out, const void* qkv, const float* bias_v,
+                        int32_t n_img, int32_t N, int32_t C, float scale, void* stream);
+
 /* ------------------------------------------------------------------------
  * Verifiers and selection.
  *   its_image_stats: per image mean, unbiased variance, min and the L2-

@@ -19,7 +19,7 @@ SYMBOLS = [
     "its_group_norm", "its_conv_head", "its_conv_tail", "its_conv_igemm", "its_softmax_rows",
     "its_attention_small", "its_image_stats", "its_candidate_scores", "its_argmax_first",
     "its_group_norm_apply", "its_conv_stats_parts", "its_set_pdl", "its_attention_fused", "its_head_patches",
-    "its_attention_flash",
+    "its_attention_flash", "its_attention_group",
 ]
 
 
@@ -93,6 +93,7 @@ def lib() -> C.CDLL:
     L.its_attention_small.argtypes = [vp, vp, i32, i32, i32, f32, vp]
     L.its_attention_fused.argtypes = [vp, vp, vp, vp, i32, i32, i32, f32, vp]
     L.its_attention_flash.argtypes = [vp, vp, vp, vp, i32, i32, i32, f32, vp]
+    L.its_attention_group.argtypes = [vp, vp, vp, i32, i32, i32, f32, vp]
     L.its_image_stats.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp]
     L.its_candidate_scores.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp]
     L.its_argmax_first.argtypes = [vp, vp, vp, i32, vp]

@@ -438,6 +438,16 @@ class UNetPlan:
             bvh = self._hold(bv, torch.float32)
             o = self.conv([(P, N, 0, 1, False)], [(one, 0, 0, 0)], H, W, vT.view(B, Cc, N), Cc, bias=bvh,
                           w_batch_stride=Cc * N, want_stats=False)
+        elif (N in (16, 32, 64) and Cc % 64 == 0 and Cc <= 512 and (Cc <= 256 or Cc % 128 == 0)
+              and self._impl_for([Cc], Cc) == 0 and self.fused_attention):
+            # small maps on the tensor cores: 128 / N images per tile, block-diagonal softmax mask
+            wqkv = self._hold(torch.cat([wq, wk, wv], 0), torch.float32)
+            bqk0 = self._hold(torch.cat([bq, bk, torch.zeros_like(bv)], 0), torch.float32)
+            qkv = self.conv([(a, Cc, 0, 1, False)], [(one, 0, 0, 0)], H, W, wqkv, 3 * Cc, bias=bqk0, want_stats=False)
+            o = self._new((B, H, W, Cc))
+            bvh = self._hold(bv, torch.float32)
+            self._op(self.L.its_attention_group, o.data_ptr(), qkv.data_ptr(), bvh.data_ptr(), B, N, Cc, scale,
+                     flops=4 * B * N * N * Cc, kind="attention_group")
         else:
             wqkv = self._hold(torch.cat([wq, wk, wv], 0), torch.float32)
             bqkv = self._hold(torch.cat([bq, bk, bv], 0), torch.float32)

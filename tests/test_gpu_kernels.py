@@ -443,7 +443,8 @@ def test_resample_blocks(cuda_dev, built_lib, impl, kind):
 
 @pytest.mark.parametrize("impl", [1, 0], ids=["cudacore", "tcgen05"])
 @pytest.mark.parametrize("B,H,C", [(2, 16, 128), (2, 16, 64), (8, 8, 128), (8, 4, 512), (1, 32, 128), (3, 32, 64),
-                                   (2, 8, 384), (5, 32, 128), (2, 16, 384), (3, 16, 256)])
+                                   (2, 8, 384), (5, 32, 128), (2, 16, 384), (3, 16, 256), (3, 4, 512), (5, 8, 256),
+                                   (20, 4, 64)])
 def test_attention_block(cuda_dev, built_lib, impl, B, H, C):
     """AttnBlock (Model.py:145-164): tensor-core batched GEMM path for >= 128 tokens,
     one-kernel path for small maps."""
