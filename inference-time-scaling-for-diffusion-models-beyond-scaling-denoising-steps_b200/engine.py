@@ -438,9 +438,12 @@ class UNetPlan:
             bvh = self._hold(bv, torch.float32)
             o = self.conv([(P, N, 0, 1, False)], [(one, 0, 0, 0)], H, W, vT.view(B, Cc, N), Cc, bias=bvh,
                           w_batch_stride=Cc * N, want_stats=False)
-        elif (N in (16, 32, 64) and Cc % 64 == 0 and Cc <= 512 and (Cc <= 256 or Cc % 128 == 0)
+        elif (N in (32, 64) and Cc % 64 == 0 and Cc <= 512 and (Cc <= 256 or Cc % 128 == 0)
               and self._impl_for([Cc], Cc) == 0 and self.fused_attention):
-            # small maps on the tensor cores: 128 / N images per tile, block-diagonal softmax mask
+            # small maps on the tensor cores: 128 / N images per tile, block-diagonal softmax mask.  (4x4 maps
+            # stay on the CUDA-core kernel: at the design batch they are only 8 tiles, a latency-bound chain
+            # of 13.6 us against 8.7 us for one CTA per query; the choice depends on the shape only, never on
+            # the batch, so a candidate's numbers do not depend on what it is batched with.)
             wqkv = self._hold(torch.cat([wq, wk, wv], 0), torch.float32)
             bqk0 = self._hold(torch.cat([bq, bk, torch.zeros_like(bv)], 0), torch.float32)
             qkv = self.conv([(a, Cc, 0, 1, False)], [(one, 0, 0, 0)], H, W, wqkv, 3 * Cc, bias=bqk0, want_stats=False)

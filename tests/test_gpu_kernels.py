@@ -499,6 +499,24 @@ def test_attention_v_transposed_operand_path_matches_mn_major_path(cuda_dev, bui
     check_close(outs[0], outs[1], 4e-3, "mn-major vs V^T")
 
 
+@pytest.mark.parametrize("n_img,N,C", [(8, 16, 512), (3, 16, 64), (19, 16, 128), (5, 32, 256), (4, 64, 384), (9, 64, 512)])
+def test_attention_group_kernel_vs_torch(cuda_dev, built_lib, n_img, N, C):
+    """its_attention_group directly (the engine uses it for 8x8 maps only): 128 / N images per tile with
+    a block-diagonal softmax mask, ragged last group included."""
+    from its_b200 import _lib
+    g = torch.Generator().manual_seed(n_img * 1000 + N + C)
+    qkv = (torch.randn(n_img, N, 3 * C, generator=g) * 1.5).to(cuda_dev).to(torch.bfloat16)
+    bias = torch.randn(C, generator=g).to(cuda_dev)
+    out = torch.full((n_img, N, C), float("nan"), dtype=torch.bfloat16, device=cuda_dev)
+    scale = float(C) ** -0.5
+    _lib.check(built_lib.its_attention_group(out.data_ptr(), qkv.data_ptr(), bias.data_ptr(), n_img, N, C, scale,
+                                             _lib.stream_ptr()), "its_attention_group")
+    q, k, v = (t.float() for t in qkv.split(C, dim=-1))
+    p = torch.softmax(torch.bmm(q, k.transpose(1, 2)) * scale, dim=-1)
+    ref = torch.bmm(p.to(torch.bfloat16).float(), v) + bias
+    check_close(out.float(), ref, 1.2e-2, "attention_group")
+
+
 def test_softmax_rows(cuda_dev, built_lib):
     from its_b200 import _lib
     s = torch.randn(300, 256, device=cuda_dev) * 4
