@@ -16,15 +16,18 @@ Cout = int(sys.argv[3]) if len(sys.argv) > 3 else 128
 B = int(sys.argv[4]) if len(sys.argv) > 4 else 64
 bn = int(sys.argv[5]) if len(sys.argv) > 5 else 0
 split = int(sys.argv[6]) if len(sys.argv) > 6 else 0
+force = int(sys.argv[7]) if len(sys.argv) > 7 else 0       # forced split-K factor (with bn)
 dev = torch.device("cuda:0")
 x = torch.randn(B, H, H, Cin, device=dev).to(torch.bfloat16)
 w = pack_conv_weight(torch.randn(Cout, Cin, 3, 3, device=dev) / 30).to(torch.bfloat16).contiguous()
 bias = torch.randn(Cout, device=dev)
 plan = UNetPlan.scratch(dev, B, 0)
 plan.split_k, plan.schedule = bool(split), 2
+if force:
+    plan._persist_plan = lambda *a, **k: (bn, force)
 out = plan.conv([(x, Cin, 0, 1, False)], [(taps_square(3), 0, 0, 0)], H, H, w, Cout, bias=bias)
 d = plan.descs[0]
-if bn:
+if bn and not force:
     d.bn = bn
 print('bn', d.bn, 'splits', d.splits)
 dbg = torch.zeros(256, 64, dtype=torch.int64, device=dev)
@@ -39,6 +42,14 @@ t = dbg.cpu().numpy()
 t = t[t[:, 0] != 0]
 clk = 1.9
 print(f"H={H} Cin={Cin} Cout={Cout} B={B} bn={bn}: {len(t)} CTAs, kernel {e0.elapsed_time(e1)*1e3:.1f} us (eager, incl. launch)")
+g = torch.cuda.CUDAGraph()
+d.dbg = None
+with torch.cuda.graph(g):
+    for _ in range(20):
+        plan.run()
+g.replay(); torch.cuda.synchronize()
+e0.record(); g.replay(); e1.record(); torch.cuda.synchronize()
+print(f"steady state (20 launches in a graph): {e0.elapsed_time(e1)*1e3/20:.2f} us per launch")
 g0 = t[:, 0].min()
 ntile = int((t[0, 8:16] != 0).sum())
 print("cta sm start_us setup_us | per tile: acc_complete_us / epilogue_done_us ... | end_us")

@@ -252,6 +252,47 @@ def test_random_search_philox_population(cuda_dev):
     assert len(ph["scores"]) == 3 and math.isfinite(pscore)
 
 
+@pytest.mark.parametrize("name", ["u_A", "c_C", "u_E"])
+def test_full_size_trajectory_properties(cuda_dev, name):
+    """BASELINE.json's full configurations (A: T=1000 at 32x32, C: guided w=1.8, E: T=2000 at 64x64) through
+    size-independent properties: a population evaluated as one batch equals the same candidates evaluated in
+    shards with their global ids (what the multi-GPU path relies on), replays are deterministic, samples are
+    finite and clipped, the verifier kernels agree with the formulas of search/verifier.py on the finished
+    samples, and the selection is the first maximum."""
+    cfg = cases.FORWARD_CASES[name]
+    net, _ = build_shell(cfg, cuda_dev)
+    if cfg["kind"] == "uncond":
+        from its_b200.Diffusion import GaussianDiffusionSampler
+        smp = GaussianDiffusionSampler(net, 1e-4, 0.02, cfg["T"]).to(cuda_dev)
+    else:
+        from its_b200.DiffusionFreeGuidence import GaussianDiffusionSampler
+        smp = GaussianDiffusionSampler(net, 1e-4, 0.02, cfg["T"], w=1.8).to(cuda_dev)
+    smp.print_steps = False
+    from its_b200.search import search_algorithm as S
+    from its_b200.search import verifier as V
+    n = 8 if name == "u_E" else 12
+    S_img = cfg["img"]
+    x_T = S.philox_normal((n, 3, S_img, S_img), 77, 0, S.TAG_X_T, cuda_dev)
+    labels = None if cfg["kind"] == "uncond" else (1 + torch.arange(n, device=cuda_dev) % 10)
+    call = (lambda x, lab, **kw: smp(x, **kw)) if labels is None else (lambda x, lab, **kw: smp(x, lab, **kw))
+    whole = call(x_T, labels, seed=5, cand_id0=0)
+    again = call(x_T, labels, seed=5, cand_id0=0)
+    assert torch.equal(whole, again)
+    h = n // 2
+    shards = torch.cat([call(x_T[:h], None if labels is None else labels[:h], seed=5, cand_id0=0),
+                        call(x_T[h:], None if labels is None else labels[h:], seed=5, cand_id0=h)])
+    assert torch.equal(whole, shards)
+    assert torch.isfinite(whole).all() and whole.abs().max().item() <= 1.0
+    assert not torch.equal(whole[0], whole[1])
+    flat = whole.flatten(1)
+    for ver, ref in ((V.OracleVerifier(), 1.0 / (1.0 + flat.var(dim=1))),
+                     (V.AestheticPredictor(), 2.0 * ((flat + 1) / 2 if whole.min() < 0 else flat).std(dim=1))):
+        got = ver.score_candidates(whole, 1)
+        assert (got - ref).abs().max().item() <= 1e-4, type(ver).__name__
+        idx, val = S.argmax_first(got)
+        assert idx == int(torch.argmax(got)) and val == float(got.max())
+
+
 def test_path_search_restart_continues_the_pivot_trajectory(cuda_dev):
     """restart=True with zero perturbation: path 0 (global candidate 0) is the pivot's own trajectory cut
     at injection_step and resumed, so its score equals the uncut trajectory's, bit for bit."""
