@@ -13,13 +13,13 @@
 // One CTA per (image, 128-query tile).  The score matrix and the probabilities never touch
 // global memory (the unfused path writes 4 N^2 bytes of fp32 scores per image and reads them
 // back twice).  Unlike the N = 256 kernel (attention_sm100.cu) the running output is kept in
-// the registers of a second warpgroup — each block's P_j V_j lands in its own TMEM buffer — so
-// no TMEM read-modify-write is needed when the running maximum moves.
+// registers — each block's P_j V_j lands in its own TMEM buffer and is folded in one block later —
+// so no TMEM read-modify-write is needed when the running maximum moves.
 //
 // Warp roles: warp 0 = TMA producer (Q once; then K_0, K_1, V_0, K_2, V_1, ... through a 3-slot
 // ring), warp 1 = MMA issuer (S_{j+1} is issued before P_j V_j, so the tensor pipe computes the
-// next scores while the softmax warps work on the current ones), warps 2..5 = softmax (thread =
-// query row), warps 6..9 = output accumulation (thread = query row, C fp32 registers).
+// next scores while the softmax warps work on the current ones), warps 2..9 = softmax + output
+// accumulation (thread = (query row, half): 64 keys of every block, C/2 fp32 output registers).
 // TMEM: S double buffered at columns [0,128) / [128,256); T at [256,256+C) / [384,384+C).
 #include "tapgemm.cuh"
 #include "sm100_ptx.cuh"
@@ -38,8 +38,8 @@ struct FlashSmem {
   static constexpr int P_BYTES = 128 * FL_KB * 2;          // 2 panels x 16 KB
   static constexpr int RING_OFF = Q_BYTES;
   static constexpr int P_OFF = RING_OFF + FL_STAGES * STAGE_BYTES;
-  static constexpr int X_OFF = P_OFF + 2 * P_BYTES;        // alpha[4][128], l[128] floats
-  static constexpr int BAR_OFF = X_OFF + 5 * 128 * 4;
+  static constexpr int X_OFF = P_OFF + 2 * P_BYTES;        // row-max exchange [2][2][128], row sums [2][128] floats
+  static constexpr int BAR_OFF = X_OFF + 6 * 128 * 4;
   static constexpr int TOTAL = BAR_OFF + FL_NBARS * 8 + 16;
 };
 
@@ -62,8 +62,8 @@ attention_flash_kernel(const FlashParams p, const __grid_constant__ CUtensorMap 
   uint8_t* q_smem = smem;
   uint8_t* ring = smem + L::RING_OFF;
   uint8_t* p_smem = smem + L::P_OFF;
-  float* alpha_s = reinterpret_cast<float*>(smem + L::X_OFF);    // [4][128]
-  float* l_s = alpha_s + 4 * 128;                                // [128]
+  float* alpha_s = reinterpret_cast<float*>(smem + L::X_OFF);    // row-max exchange [2 buffers][2 halves][128]
+  float* l_s = alpha_s + 4 * 128;                                // partial row sums [2 halves][128]
   uint64_t* q_full = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
   uint64_t* full_bar = q_full + 1;
   uint64_t* empty_bar = full_bar + FL_STAGES;
@@ -88,11 +88,11 @@ attention_flash_kernel(const FlashParams p, const __grid_constant__ CUtensorMap 
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&s_full[b], 1);
-      mbar_init(&s_free[b], 128);
-      mbar_init(&p_full[b], 128);
+      mbar_init(&s_free[b], 256);
+      mbar_init(&p_full[b], 256);
       mbar_init(&p_free[b], 1);
       mbar_init(&t_full[b], 1);
-      mbar_init(&t_free[b], 128);
+      mbar_init(&t_free[b], 256);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     tma_prefetch_desc(&tmQ);
@@ -215,25 +215,36 @@ attention_flash_kernel(const FlashParams p, const __grid_constant__ CUtensorMap 
         ++it;
       }
     }
-  } else if (warp < 6) {
-    // ---------------------------------------------------- softmax -----
+  } else {
+    // ------------------------------- softmax + output accumulation -----
+    // thread = (query row, half): the 64 keys [half*64, half*64+64) of every block for the softmax and
+    // the C/2 channels [half*C/2, ...) of the running output.  Two threads per row keep two warps per
+    // scheduler busy (one warp per scheduler left the MUFU / issue latency exposed: 4000 clocks per
+    // block against 1570 of tensor work); the row maximum is exchanged through shared memory.
     const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int row = q * 32 + lane;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
-    float m = -INFINITY, l = 0.f;
+    constexpr int CH = C / 2;                     // output channels per thread
+    float o[CH];
+#pragma unroll
+    for (int i = 0; i < CH; ++i) o[i] = 0.f;
+    float m = -INFINITY, l = 0.f, alpha_prev = 0.f;
     for (int j = 0; j < NB; ++j) {
       const uint32_t b = j & 1u, use = (uint32_t)(j >> 1);
       mbar_wait(&s_full[b], use & 1u);
       tcgen05_fence_after();
+      // this thread's 64 scores of the block stay in registers between the maximum and the exponentials
+      uint32_t v[64];
+      tmem_ld32_nowait(lane_addr + b * 128 + (uint32_t)(half * 64), v);
+      tmem_ld32_nowait(lane_addr + b * 128 + (uint32_t)(half * 64 + 32), v + 32);
+      tmem_wait_ld();
       float mx = m;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld32_nowait(lane_addr + b * 128 + (uint32_t)(c * 32), v);
-        tmem_wait_ld();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
-      }
+      for (int i = 0; i < 64; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+      alpha_s[(b * 2 + half) * 128 + row] = mx;
+      named_bar_sync(2, 256);
+      mx = fmaxf(mx, alpha_s[(b * 2 + (half ^ 1)) * 128 + row]);
       const float moff = mx * p.scale_log2e;
       float alpha;
       {
@@ -242,16 +253,10 @@ attention_flash_kernel(const FlashParams p, const __grid_constant__ CUtensorMap 
       }
       mbar_wait(&p_free[b], (use & 1u) ^ 1u);                // P V_{j-2} has consumed this buffer
       float sum = 0.f;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld32_nowait(lane_addr + b * 128 + (uint32_t)(c * 32), v);
-        tmem_wait_ld();
-        const int key0 = c * 32;
-        const int panel = key0 >> 6, chunk0 = (key0 & 63) >> 3;
-        const uint32_t row_addr = smem_u32(p_smem + b * L::P_BYTES + panel * 16384) + (uint32_t)row * 128u;
+      {
+        const uint32_t row_addr = smem_u32(p_smem + b * L::P_BYTES + half * 16384) + (uint32_t)row * 128u;   // panel = half
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
+        for (int g = 0; g < 8; ++g) {
           float f[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
@@ -263,7 +268,7 @@ attention_flash_kernel(const FlashParams p, const __grid_constant__ CUtensorMap 
           unpack8(pk, r);                  // the row sum is taken over the rounded values the MMA reads
 #pragma unroll
           for (int i = 0; i < 8; ++i) sum += r[i];
-          const uint32_t dst = row_addr + (uint32_t)(((chunk0 + g) ^ (row & 7)) << 4);
+          const uint32_t dst = row_addr + (uint32_t)((g ^ (row & 7)) << 4);
           const uint4 u = *reinterpret_cast<const uint4*>(&pk);
           asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(u.x), "r"(u.y), "r"(u.z), "r"(u.w)
                        : "memory");
@@ -271,67 +276,68 @@ attention_flash_kernel(const FlashParams p, const __grid_constant__ CUtensorMap 
       }
       l = fmaf(l, alpha, sum);
       m = mx;
-      alpha_s[(j & 3) * 128 + row] = alpha;
       tcgen05_fence_before();
       mbar_arrive(&s_free[b]);
       fence_proxy_async_smem();
       mbar_arrive(&p_full[b]);
+      if (j >= 1) {
+        // deferred by one block: T_{j-1} = P_{j-1} V_{j-1} has had the whole softmax of block j to finish
+        const uint32_t bt = (j - 1) & 1u, uset = (uint32_t)((j - 1) >> 1);
+        mbar_wait(&t_full[bt], uset & 1u);
+        tcgen05_fence_after();
+#pragma unroll
+        for (int c = 0; c < CH / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld32_nowait(lane_addr + 256u + bt * 128 + (uint32_t)(half * CH + c * 32), v);
+          tmem_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o[c * 32 + i] = fmaf(o[c * 32 + i], alpha_prev, __uint_as_float(v[i]));
+        }
+        tcgen05_fence_before();
+        mbar_arrive(&t_free[bt]);
+      }
+      alpha_prev = alpha;
     }
-    l_s[row] = l;
-    named_bar_sync(2, 256);                                  // row sums visible to the output warps
-  } else {
-    // ------------------------------------------ output accumulation ----
-    const int q = warp & 3;
-    const int row = q * 32 + lane;
-    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + 256u;
-    float o[C];
-#pragma unroll
-    for (int i = 0; i < C; ++i) o[i] = 0.f;
-    for (int j = 0; j < NB; ++j) {
-      const uint32_t b = j & 1u, use = (uint32_t)(j >> 1);
-      // alpha_j was written before the softmax warps' p_full arrival, which the MMA warp acquired
-      // before issuing P_j V_j; four alpha slots, because the softmax warps may run up to two blocks
-      // ahead of this warpgroup (block j+4 cannot be staged before T_{j+2}, i.e. before t_free of j).
-      // (No wait on p_full here: this warpgroup may lag that barrier by two phases.)
-      mbar_wait(&t_full[b], use & 1u);
+    {
+      const uint32_t bt = (NB - 1) & 1u, uset = (uint32_t)((NB - 1) >> 1);
+      mbar_wait(&t_full[bt], uset & 1u);
       tcgen05_fence_after();
-      const float alpha = alpha_s[(j & 3) * 128 + row];
 #pragma unroll
-      for (int c = 0; c < C / 32; ++c) {
+      for (int c = 0; c < CH / 32; ++c) {
         uint32_t v[32];
-        tmem_ld32_nowait(lane_addr + b * 128 + (uint32_t)(c * 32), v);
+        tmem_ld32_nowait(lane_addr + 256u + bt * 128 + (uint32_t)(half * CH + c * 32), v);
         tmem_wait_ld();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) o[c * 32 + i] = fmaf(o[c * 32 + i], alpha, __uint_as_float(v[i]));
+        for (int i = 0; i < 32; ++i) o[c * 32 + i] = fmaf(o[c * 32 + i], alpha_prev, __uint_as_float(v[i]));
       }
-      tcgen05_fence_before();
-      mbar_arrive(&t_free[b]);
     }
+    l_s[half * 128 + row] = l;
     named_bar_sync(2, 256);
-    const float inv = 1.0f / l_s[row];
-    // every S MMA has completed long ago: the Q panels are free and become the output staging
+    const float inv = 1.0f / (l + l_s[(half ^ 1) * 128 + row]);
+    // every MMA has completed: the Q panels are free and become the output staging
     uint8_t* stg = q_smem;
 #pragma unroll
-    for (int g = 0; g < C / 8; ++g) {
+    for (int g = 0; g < CH / 8; ++g) {
+      const int col0 = half * CH + g * 8;
       float f[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) f[i] = o[g * 8 + i] * inv;
       if (p.bias_v) {
-        const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias_v + g * 8));
-        const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias_v + g * 8 + 4));
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias_v + col0));
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias_v + col0 + 4));
         f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
         f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
       }
       const bf16x8 pk = pack8(f);
-      const int panel = g >> 3, chunk = g & 7;
+      const int panel = col0 >> 6, chunk = (col0 & 63) >> 3;
       const uint32_t dst = smem_u32(stg + panel * 16384) + (uint32_t)row * 128u + (uint32_t)((chunk ^ (row & 7)) << 4);
       const uint4 u = *reinterpret_cast<const uint4*>(&pk);
       asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(u.x), "r"(u.y), "r"(u.z), "r"(u.w)
                    : "memory");
     }
     fence_proxy_async_smem();
-    named_bar_sync(3, 128);
-    if (warp == 6 && lane == 0) {
+    named_bar_sync(2, 256);
+    if (warp == 2 && lane == 0) {
       for (int pn = 0; pn < NKC; ++pn) tma_store_3d(&tmO, stg + pn * 16384, pn * 64, qt * 128, img);
       bulk_commit_group();
       bulk_wait_group<0>();
