@@ -95,6 +95,7 @@ class UNetPlan:
         self.ws_persist, self.sm_count, self.fused_attention = None, 148, True
         self.head_on_tensor_cores = True
         self.attn_v_mn = _os.environ.get("ITS_ATTN_VT", "0") != "1"
+        self.fork_time_chain, self._side = False, None
         self.gn_dtype = FP16 if (FP16_GN and impl != 1) else BF16
         return self
 
@@ -225,6 +226,8 @@ class UNetPlan:
         d.out, d.out_fp32 = out.data_ptr(), int(out_fp32)
         d.Hout, d.Wout, d.out_scale, d.out_c_pitch, d.out_c_off = Hout, Wout, out_scale, out.shape[-1], 0
         d.bias = _ptr(bias)
+        if vec is not None and getattr(self, "_join_at", 0) is None:
+            self._join_at = len(self.ops)       # first consumer of the projected time embedding
         if vec is not None:
             d.vec, d.vec_stride, d.vec_off = vec.data_ptr(), (0 if vec.shape[0] == 1 else vec.shape[1]), vec_off
         if vec2 is not None:
@@ -556,6 +559,8 @@ class UNetPlan:
         self.fused_attention = _os.environ.get("ITS_FUSED_ATTENTION", "1") != "0"
         self.head_on_tensor_cores = _os.environ.get("ITS_HEAD_TC", "1") != "0"
         self.attn_v_mn = _os.environ.get("ITS_ATTN_VT", "0") != "1"
+        self.fork_time_chain = _os.environ.get("ITS_FORK_TIME", "1") != "0"
+        self._side = None
         self.gn_dtype = FP16 if (FP16_GN and ch % 64 == 0 and self.impl_forced != 1) else BF16
         self.x_in = self._new((self.n_img_in, 3, H, W), torch.float32)
         self.t_dev = torch.zeros(1, dtype=torch.int32, device=self.dev)
@@ -586,6 +591,11 @@ class UNetPlan:
         wt = self._hold(torch.cat([rb.temb_proj[1].weight.detach().float() for rb in blocks], 0), torch.float32)
         bt = self._hold(torch.cat([rb.temb_proj[1].bias.detach().float() for rb in blocks], 0), torch.float32)
         self.tproj = self.linear(temb, wt, bt, silu_in=True)
+        # The time-embedding chain (embedding -> two linears -> every temb_proj) depends on t only; the head
+        # (patch gather, head GEMM, first GroupNorm) depends on x only.  run() forks the chain onto a side
+        # stream and joins before the first launch that adds the projected embedding.
+        self._n_time_ops = len(self.ops)
+        self._join_at = None
         self.cproj = None
         if self.cond:
             # Everything from the label embedding to the per-ResBlock cond_proj vectors is a function of
@@ -645,10 +655,32 @@ class UNetPlan:
                 _lib.check(rc, fn.__name__)
 
     def run(self) -> None:
-        """Enqueue every launch on the current stream (graph-capturable)."""
+        """Enqueue every launch on the current stream (graph-capturable).  The time-embedding chain runs
+        on a side stream next to the head of the network (fork / join by events, so the pair is two
+        parallel branches of the captured step graph)."""
         s = _lib.stream_ptr()
-        L = self.L
-        for fn, args in self.ops:
+        n_time = getattr(self, "_n_time_ops", 0)
+        join_at = getattr(self, "_join_at", None)
+        fork = self.fork_time_chain and n_time > 0 and join_at is not None and join_at > n_time
+        if fork:
+            if self._side is None:
+                self._side = torch.cuda.Stream(device=self.dev)
+                self._ev_fork, self._ev_join = torch.cuda.Event(), torch.cuda.Event()
+            main = torch.cuda.current_stream()
+            self._ev_fork.record(main)
+            self._side.wait_event(self._ev_fork)
+            s_side = self._side.cuda_stream
+            for fn, args in self.ops[:n_time]:
+                rc = fn(*args, s_side)
+                if rc != 0:
+                    _lib.check(rc, fn.__name__)
+            self._ev_join.record(self._side)
+        for i, (fn, args) in enumerate(self.ops):
+            if fork:
+                if i < n_time:
+                    continue
+                if i == join_at:
+                    torch.cuda.current_stream().wait_event(self._ev_join)
             rc = fn(*args, s)
             if rc != 0:
                 _lib.check(rc, fn.__name__)
