@@ -180,7 +180,8 @@ extern "C" int its_attention_small(void* out, const void* qkv, int32_t n_img, in
   ITS_REQUIRE(out && qkv, "its_attention_small: null pointer");
   ITS_REQUIRE(n_img > 0 && n_img <= 65535 && N > 0 && N <= 64 && C > 0 && C % 8 == 0,
               "its_attention_small: unsupported N=%d C=%d n_img=%d", N, C, n_img);
-  if (N <= 32) {
+  const size_t smem_need = (size_t)3 * N * (C + 8) * 2 + 8 * its::AS_QB * 64 * 4;
+  if (N <= 32 || smem_need > 227 * 1024) {      // tiny maps, or q|k|v of one image do not fit shared memory (C = 1024)
     ITS_REQUIRE(n_img <= 65535, "its_attention_small: n_img");
     ITS_LAUNCH(its::attention_tiny_kernel, dim3(N, n_img), dim3(256), 0, its::as_stream(stream),
                static_cast<__nv_bfloat16*>(out), static_cast<const __nv_bfloat16*>(qkv), N, C, scale);

@@ -500,7 +500,29 @@ tapgemm_persist_kernel(const __grid_constant__ TapGemmParams p, const __grid_con
         }
         fence_proxy_async_smem();
         mbar_arrive(&pfull_bar[sb]);
-        if (p.stats != nullptr) {
+        if (p.stats != nullptr && p.bb > 8) {
+          // maps smaller than 4x4 (fewer than 16 rows per image: MainCondition.py's 2x2 / 1x1 levels): the
+          // 16-row sub-block scheme below does not apply; sum each image's rows directly (tiny work)
+          mbar_wait(&pfull_bar[sb], spar);
+          for (int idx = et; idx < p.bb * 16; idx += P_EPI_THREADS) {
+            const int ib = idx >> 4, ch = idx & 15;
+            const int bi = c.tb * p.bb + ib;
+            if (bi >= p.B) continue;
+            float s = 0.f, qq = 0.f;
+            for (int r = ib * rpi; r < (ib + 1) * rpi; ++r) {
+              const uint32_t a = smem_u32(sbuf) + (uint32_t)r * 128u +
+                                 (uint32_t)((((ch >> 1) ^ (r & 7)) << 4) | ((ch & 1) << 3));
+              uint32_t w0, w1;
+              asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(w0), "=r"(w1) : "r"(a));
+              const float x0 = __uint_as_float(w0 << 16), x1 = __uint_as_float(w0 & 0xffff0000u);
+              const float x2 = __uint_as_float(w1 << 16), x3 = __uint_as_float(w1 & 0xffff0000u);
+              s += (x0 + x1) + (x2 + x3);
+              qq = fmaf(x0, x0, qq); qq = fmaf(x1, x1, qq); qq = fmaf(x2, x2, qq); qq = fmaf(x3, x3, qq);
+            }
+            reinterpret_cast<float2*>(p.stats)[((long long)bi * p.stats_parts + c.phase) * (p.Cout >> 2) + (n >> 2) + ch] =
+                make_float2(s, qq);
+          }
+        } else if (p.stats != nullptr) {
           mbar_wait(&pfull_bar[sb], spar);       // every thread's part of the panel is staged
           if (prev_dst != nullptr) {             // final reduce of the previous panel's sub-block sums
             const float2* rd = red + ((pc + 1) & 1u) * 128;

@@ -439,8 +439,10 @@ extern "C" int its_group_norm_apply(void* out, const void* src0, int32_t C0, con
   ITS_REQUIRE(out && src0 && stats0 && gamma && beta, "its_group_norm_apply: null pointer");
   ITS_REQUIRE(C1 == 0 || (src1 != nullptr && stats1 != nullptr), "its_group_norm_apply: C1 > 0 needs src1 and stats1");
   const int C = C0 + C1;
-  ITS_REQUIRE(C0 > 0 && C0 % 8 == 0 && C1 % 8 == 0 && C <= 8 * GN_MAX_VEC,
-              "its_group_norm_apply: channels (%d+%d) must be multiples of 8 and <= %d", C0, C1, 8 * GN_MAX_VEC);
+  // one thread per 8-channel vector of a pixel row: up to GN_THREADS vectors (the 1024+1024 concatenations of
+  // MainCondition.py's default widths)
+  ITS_REQUIRE(C0 > 0 && C0 % 8 == 0 && C1 % 8 == 0 && C <= 8 * GN_THREADS,
+              "its_group_norm_apply: channels (%d+%d) must be multiples of 8 and <= %d", C0, C1, 8 * GN_THREADS);
   ITS_REQUIRE(groups > 0 && groups <= 64 && (groups & (groups - 1)) == 0 && C % groups == 0 && (C / groups) % 4 == 0,
               "its_group_norm_apply: groups=%d must be a power of two dividing C=%d into multiples of 4 channels", groups, C);
   ITS_REQUIRE(n_img > 0 && HW > 0 && parts0 > 0 && (C1 == 0 || parts1 > 0), "its_group_norm_apply: bad n_img/HW/parts");

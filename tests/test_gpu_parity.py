@@ -57,6 +57,25 @@ def test_unet_forward_full_size_vs_reference(cuda_dev, name):
     assert rel_err(eps, ref) < 8e-2
 
 
+@pytest.mark.parametrize("kind,mult,img,B", [("cond", [1, 2, 2, 2], 8, 5), ("cond", [1, 2, 2, 2, 2], 32, 3),
+                                             ("uncond", [1, 2, 2, 2], 16, 4)])
+def test_unet_forward_down_to_1x1_maps_vs_oracle(cuda_dev, kind, mult, img, B):
+    """Deep nets whose coarsest maps are 2x2 or 1x1 (MainCondition.py's own defaults have six levels at
+    32x32): fewer than 16 rows per image in a GEMM tile, 1- and 4-token attention, 5x5 / transposed convs on
+    1x1 maps.  Against the pinned CPU oracle (scripts/stretch_maincondition.py runs the full 547 M default)."""
+    cfg = dict(kind=kind, T=100, ch=64, ch_mult=mult, attn=[1, 3], num_res_blocks=1, dropout=0.0, num_labels=10,
+               weight_seed=41, img=img, B=B, input_seed=141)
+    net, sd = build_shell(cfg, cuda_dev)
+    x, t, labels = cases.forward_inputs(cfg)
+    args = (x.to(cuda_dev), t.to(cuda_dev)) + ((labels.to(cuda_dev),) if labels is not None else ())
+    eps = net(*args).cpu()
+    with torch.no_grad():
+        ref = O.unet_forward(sd, x, t, labels)
+    assert torch.isfinite(eps).all()
+    assert rms_err(eps, ref) < 2e-2, (rms_err(eps, ref), rel_err(eps, ref))
+    assert rel_err(eps, ref) < 8e-2
+
+
 def test_unet_forward_is_batch_invariant_and_deterministic(cuda_dev):
     """A candidate's eps must not depend on which batch / rank evaluates it."""
     cfg = cases.FORWARD_CASES["u_3lvl"]
