@@ -141,3 +141,27 @@ def test_config_driven_search_and_grid(cuda_dev, built_lib, tmp_path):
         assert b is not None and np.isfinite(s) and im.abs().max().item() <= 1.0
     out = I.save_image_grid(images, str(tmp_path / "grid" / "s.png"), nrow=2)
     assert os.path.getsize(out) > 100
+
+
+def test_repo_config_file_parses():
+    from its_b200 import inference as I
+    from tests.conftest import ROOT
+    cfg = I.load_config(os.path.join(ROOT, "config", "inference_config.yaml"), ["T=8", "search.n_candidates=3"])
+    assert cfg["T"] == 8 and cfg["channel_mult"] == [1, 2, 3, 4] and cfg["checkpoint_path"] is None
+    assert cfg["search"]["n_candidates"] == 3 and cfg["search"]["algorithm"] == "random"
+
+
+@pytest.mark.gpu
+def test_cli_main_end_to_end(cuda_dev, built_lib, tmp_path, capsys):
+    """`python -m its_b200.inference <yaml> key=value ...` from the repo's config file: search, then sampling with
+    metrics tracking, image grids written."""
+    from its_b200 import inference as I
+    from tests.conftest import ROOT
+    cfg_path = os.path.join(ROOT, "config", "inference_config.yaml")
+    small = ["T=8", "img_size=16", "channel=64", "channel_mult=[1,2]", "num_res_blocks=1", "dropout=0.0", "batch_size=2",
+             f"sampled_images_save_dir={tmp_path}", "nrow=2"]
+    assert I.main([cfg_path] + small + ["search.n_candidates=4"]) == 0
+    assert "search: best score" in capsys.readouterr().out
+    assert I.main([cfg_path] + small + ["search=null", "metric_interval=3"]) == 0
+    assert "metric points" in capsys.readouterr().out
+    assert any(f.endswith(".png") for f in os.listdir(tmp_path))
