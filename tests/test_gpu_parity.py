@@ -76,6 +76,23 @@ def test_unet_forward_down_to_1x1_maps_vs_oracle(cuda_dev, kind, mult, img, B):
     assert rel_err(eps, ref) < 8e-2
 
 
+@pytest.mark.parametrize("kind,ch,mult,img,B", [("uncond", 32, [1, 2], 8, 3), ("cond", 32, [1, 2], 8, 3),
+                                                ("uncond", 96, [1, 2, 2], 16, 2), ("cond", 160, [1, 2], 16, 2)])
+def test_unet_forward_widths_off_the_64_channel_grid_vs_oracle(cuda_dev, kind, ch, mult, img, B):
+    """Widths that are not multiples of 64 (ch = 32 is the smallest GroupNorm(32, ch) allows): layers whose
+    channel counts do not fill 64-deep k-blocks run on the CUDA-core twins, the rest on tcgen05, in one plan."""
+    cfg = dict(kind=kind, T=50, ch=ch, ch_mult=mult, attn=[1], num_res_blocks=1, dropout=0.0, num_labels=10,
+               weight_seed=51, img=img, B=B, input_seed=151)
+    net, sd = build_shell(cfg, cuda_dev)
+    x, t, labels = cases.forward_inputs(cfg)
+    args = (x.to(cuda_dev), t.to(cuda_dev)) + ((labels.to(cuda_dev),) if labels is not None else ())
+    eps = net(*args).cpu()
+    with torch.no_grad():
+        ref = O.unet_forward(sd, x, t, labels)
+    assert torch.isfinite(eps).all()
+    assert rms_err(eps, ref) < 2e-2 and rel_err(eps, ref) < 8e-2, (rms_err(eps, ref), rel_err(eps, ref))
+
+
 def test_unet_forward_is_batch_invariant_and_deterministic(cuda_dev):
     """A candidate's eps must not depend on which batch / rank evaluates it."""
     cfg = cases.FORWARD_CASES["u_3lvl"]
