@@ -21,8 +21,9 @@ the global best (:193-196), PathSearch is the reference's placeholder (perturb
 x_T, denoise fully, :307-316) unless `restart=True` is passed (opt-in extension:
 true mid-trajectory restart at `injection_step`).
 
-GradientBasedSearch (:343-438) needs autograd through the whole trajectory and
-is outside the sampling path.
+GradientBasedSearch (:343-438) needs autograd through the whole trajectory: it is kept
+for arbitrary differentiable callables (callable mode only, the reference's loop); the
+kernel sampler is not differentiable and is refused with a clear error.
 """
 from __future__ import annotations
 
@@ -387,6 +388,46 @@ class PathSearch:
         idx, val = argmax_first(scores)
         if idx >= 0:
             best_score, best_noise = val, perturbed(idx, idx + 1)[0].clone()
+        return best_noise, best_score, history
+
+    def reset_nfes(self):
+        self.nfes = 0
+
+
+# ----------------------------------------------------- GradientBasedSearch --
+class GradientBasedSearch:
+    """Adam ascent on the verifier score through a DIFFERENTIABLE denoise_fn / verifier_fn pair
+    (:343-438).  Host-side torch only: the its_b200 kernel sampler has no backward pass, so a
+    `SamplerDenoiser` is refused; any autograd-capable callables work as in the reference."""
+
+    def __init__(self, n_iterations: int = 20, lr: float = 0.01, verbose: bool = False):
+        self.n_iterations = n_iterations
+        self.lr = lr
+        self.verbose = verbose
+        self.nfes = 0
+
+    def search(self, initial_noise: torch.Tensor, denoise_fn: Callable, verifier_fn: Callable,
+               device: str = 'cuda', **kwargs) -> Tuple[torch.Tensor, float, Dict[str, Any]]:
+        if isinstance(denoise_fn, SamplerDenoiser):
+            raise TypeError("GradientBasedSearch differentiates through denoise_fn; the its_b200 kernel sampler "
+                            "is inference-only (use RandomSearch / ZeroOrderSearch / PathSearch with it)")
+        noise = initial_noise.clone().requires_grad_(True)
+        opt = torch.optim.Adam([noise], lr=self.lr)
+        history: Dict[str, Any] = {'scores': [], 'grad_norms': []}
+        best_noise, best_score = noise.clone(), float('-inf')
+        for it in range(self.n_iterations):
+            opt.zero_grad()
+            score = verifier_fn(denoise_fn(noise, **kwargs), **kwargs)
+            self.nfes += 1
+            (-score).backward()                               # maximise the score
+            history['grad_norms'].append(noise.grad.norm().item())
+            opt.step()                                        # the score recorded below belongs to the pre-step noise,
+            value = score.item() if isinstance(score, torch.Tensor) else score
+            history['scores'].append(value)
+            if value > best_score:                            # ... but, as in the reference, the stored noise is post-step
+                best_score, best_noise = value, noise.clone().detach()
+            if self.verbose:
+                print(f"Gradient-Based Search Iteration {it + 1}/{self.n_iterations}: score {value:.4f}")
         return best_noise, best_score, history
 
     def reset_nfes(self):

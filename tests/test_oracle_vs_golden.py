@@ -1,6 +1,7 @@
 """CPU: the oracle restatement against fixtures produced by the reference itself
 (tests/golden/make_golden.py), plus published known-answer vectors."""
 import math
+import os
 
 import numpy as np
 import pytest
@@ -122,3 +123,38 @@ def test_philox_known_answers():
     assert [int(v) for v in p] == [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
     x = philox.normal(7, 3, 11, 8, 4096)
     assert abs(float(x.mean())) < 0.02 and abs(float(x.std()) - 1.0) < 0.02
+
+
+def test_gradient_based_search_matches_reference_on_differentiable_callables():
+    """GradientBasedSearch (search_algorithm.py:343-438) is host-side torch over arbitrary differentiable
+    callables: same Adam trajectory, scores, gradient norms and returned noise as the reference class
+    (executed here when /root/reference is mounted; otherwise the invariants are checked)."""
+    import importlib.util
+    import contextlib
+    import io
+    from its_b200.search import search_algorithm as S
+    w = torch.linspace(-1, 1, 48).reshape(1, 3, 4, 4)
+
+    def denoise(z, **kw):
+        return torch.tanh(z * 0.7 + w)
+
+    def verify(img, **kw):
+        return -(img - 0.25).pow(2).mean()
+
+    z0 = torch.sin(torch.arange(48.0)).reshape(1, 3, 4, 4)
+    gs = S.GradientBasedSearch(n_iterations=7, lr=0.05)
+    bn, bs, hist = gs.search(z0, denoise, verify, device="cpu")
+    assert gs.nfes == 7 and len(hist["scores"]) == 7 and len(hist["grad_norms"]) == 7
+    assert hist["scores"][-1] > hist["scores"][0] and bs == max(hist["scores"])
+    ref_path = os.path.join(os.environ.get("ITS_REF_DIR", "/root/reference"), "search", "search_algorithm.py")
+    if os.path.exists(ref_path):
+        spec = importlib.util.spec_from_file_location("ref_search_gb", ref_path)
+        mod = importlib.util.module_from_spec(spec)
+        with contextlib.redirect_stdout(io.StringIO()):
+            spec.loader.exec_module(mod)
+        rg = mod.GradientBasedSearch(n_iterations=7, lr=0.05)
+        rn, rs, rh = rg.search(z0, denoise, verify, device="cpu")
+        assert rh["scores"] == hist["scores"] and rh["grad_norms"] == hist["grad_norms"]
+        assert rs == bs and torch.equal(rn, bn)
+    with pytest.raises(TypeError):
+        gs.search(z0, S.SamplerDenoiser(None), verify)
