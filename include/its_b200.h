@@ -120,7 +120,8 @@ int its_linear(float* y, const float* x, const float* W, const float* bias,
  * they are reduced, in a fixed order and in double precision, from the partial
  * sums the producing tap-GEMM wrote (its_conv_desc.stats), and the launch is one
  * streaming normalise+Swish pass (its_group_norm_apply).
- * out_fp16 != 0 stores IEEE fp16 (inputs are always bf16 feature maps).
+ * out_fp16 bit 0: store IEEE fp16 instead of bf16.  Bits 1 and 2 say that
+ * source 0 / source 1 hold IEEE fp16 (the opt-in fp16 residual stream); inputs are bf16 otherwise.
  * Deterministic (no float atomics).  chunks <= 8: ONE launch, the chunks of an
  * image form a thread-block cluster and exchange partial sums through distributed
  * shared memory; chunks > 8: two launches through `partials`, scratch of
@@ -243,6 +244,9 @@ typedef struct {
   int32_t stats_parts;   /* its_conv_stats_parts() of this descriptor     */
   int32_t schedule;      /* 0 = auto, 1 = one tile per CTA, 2 = persistent
                             CTAs (TMEM double buffer, TMA-store epilogue) */
+  int32_t out_fp16;      /* bit 0: 16-bit NHWC output in IEEE fp16 instead of bf16 (the opt-in
+                            fp16 residual stream: 3 more mantissa bits, 65504 range);
+                            bit 1: `res` holds IEEE fp16                               */
 } its_conv_desc;
 
 int its_conv_igemm(const its_conv_desc* desc_host, int32_t impl, void* stream);

@@ -51,6 +51,7 @@ class ConvDesc(C.Structure):
         ("out_nchw", C.c_int32), ("splits", C.c_int32), ("ws", C.c_void_p), ("ws_elems", C.c_int64),
         ("cluster", C.c_int32), ("dbg", C.c_void_p),
         ("stats", C.c_void_p), ("stats_parts", C.c_int32), ("schedule", C.c_int32),
+        ("out_fp16", C.c_int32),
     ]
 
 

@@ -39,7 +39,8 @@ class PlannedUNet(nn.Module):
 
     def plan(self, n_img: int, H: int, W: int, *, n_img_in: Optional[int] = None, uniform_t: bool = False,
              impl: Optional[int] = None) -> UNetPlan:
-        key = (n_img, H, W, n_img_in or n_img, uniform_t, impl, self.head.weight.data_ptr())
+        key = (n_img, H, W, n_img_in or n_img, uniform_t, impl, self.head.weight.data_ptr(),
+               bool(getattr(self, "residual_fp16", False)))
         p = self._plans.get(key)
         if p is None:
             p = UNetPlan(self, n_img, H, W, n_img_in=n_img_in, uniform_t=uniform_t, impl=impl)

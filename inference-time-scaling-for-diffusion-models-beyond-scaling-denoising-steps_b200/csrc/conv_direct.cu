@@ -208,14 +208,19 @@ __global__ void __launch_bounds__(128) tapgemm_ref_kernel(const TapGemmParams p)
   if (p.vec) v += p.vec[(long long)b * p.vec_stride + n];
   if (p.vec2) v += p.vec2[(long long)b * p.vec2_stride + n];
   const long long opix = ((long long)b * p.Hout + (y * p.out_scale + ph.py)) * p.Wout + (x * p.out_scale + ph.px);
-  if (p.res) v += __bfloat162float(p.res[opix * p.res_c_pitch + n]);
+  if (p.res)
+    v += p.res_fp16 ? __half2float(reinterpret_cast<const __half*>(p.res)[opix * p.res_c_pitch + n])
+                    : __bfloat162float(p.res[opix * p.res_c_pitch + n]);
   if (p.out_nchw)
     static_cast<float*>(p.out)[(((long long)b * p.Cout + n) * p.Hout + (y * p.out_scale + ph.py)) * p.Wout +
                                (x * p.out_scale + ph.px)] = v;
   else if (p.out_fp32)
     static_cast<float*>(p.out)[opix * p.out_c_pitch + n] = v;
   else
-    static_cast<__nv_bfloat16*>(p.out)[opix * p.out_c_pitch + n] = __float2bfloat16_rn(v);
+    if (p.out_fp16)
+      static_cast<__half*>(p.out)[opix * p.out_c_pitch + n] = __float2half_rn(v);
+    else
+      static_cast<__nv_bfloat16*>(p.out)[opix * p.out_c_pitch + n] = __float2bfloat16_rn(v);
 }
 
 int tapgemm_launch_ref(const TapGemmParams& p, cudaStream_t stream) {
@@ -294,6 +299,9 @@ int tapgemm_build_params(const its_conv_desc* d, TapGemmParams* p, bool need_k64
   p->dbg = reinterpret_cast<long long*>(d->dbg);
   p->stats = d->stats;
   p->stats_parts = d->stats_parts;
+  p->out_fp16 = d->out_fp16 & 1;            // bit 0: output format, bit 1: residual tensor format
+  p->res_fp16 = (d->out_fp16 >> 1) & 1;
+  ITS_REQUIRE(!((d->out_fp16 & 1) && (d->out_fp32 || d->out_nchw)), "its_conv_igemm: out_fp16 with an fp32 output");
   if (p->splits > 1) ITS_REQUIRE(d->ws != nullptr, "its_conv_igemm: splits=%d needs a workspace", d->splits);
   p->out_fp32 = d->out_fp32;
   p->out = d->out_fp32 ? static_cast<void*>(static_cast<float*>(d->out) + d->out_c_off)

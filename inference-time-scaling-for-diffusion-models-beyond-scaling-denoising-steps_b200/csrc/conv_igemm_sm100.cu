@@ -61,7 +61,7 @@ __device__ __forceinline__ void apply_and_store8(const TapGemmParams& p, const D
   }
   if (p.res) {
     float r[8];
-    unpack8(*reinterpret_cast<const bf16x8*>(p.res + opix * p.res_c_pitch + n), r);
+    unpack8_fmt(*reinterpret_cast<const bf16x8*>(p.res + opix * p.res_c_pitch + n), r, p.res_fp16 != 0);
 #pragma unroll
     for (int j = 0; j < 8; ++j) f[j] += r[j];
   }
@@ -70,7 +70,7 @@ __device__ __forceinline__ void apply_and_store8(const TapGemmParams& p, const D
     dst[0] = make_float4(f[0], f[1], f[2], f[3]);
     dst[1] = make_float4(f[4], f[5], f[6], f[7]);
   } else {
-    *reinterpret_cast<bf16x8*>(static_cast<__nv_bfloat16*>(p.out) + opix * p.out_c_pitch + n) = pack8(f);
+    *reinterpret_cast<bf16x8*>(static_cast<__nv_bfloat16*>(p.out) + opix * p.out_c_pitch + n) = pack8_fmt(f, p.out_fp16 != 0);
   }
 }
 

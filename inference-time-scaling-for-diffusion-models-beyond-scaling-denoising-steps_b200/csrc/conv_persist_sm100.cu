@@ -97,13 +97,72 @@ __device__ __forceinline__ WorkItem decode_item(int w, int total_tiles, int S) {
   return it;
 }
 
+// Epilogue inner loops, specialised on the 16-bit output format (H = IEEE fp16, else bf16) so that the
+// format test stays out of the unrolled loops.
+template <bool H>
+__device__ __forceinline__ void tm_stage_column(const uint32_t* v, float alpha, float bvs, uint32_t sbuf_addr, int half,
+                                                uint32_t chunk, uint32_t col_byte, float& s, float& qq) {
+#pragma unroll
+  for (int i = 0; i < 64; ++i) {
+    const uint32_t prow = (uint32_t)(half * 64 + i);          // pixel row within the 128-row box
+    const float f = fmaf(__uint_as_float(v[i]), alpha, bvs);
+    unsigned short hb;
+    float r;
+    if (H) {
+      const __half hh = __float2half_rn(f);
+      r = __half2float(hh);
+      hb = __half_as_ushort(hh);
+    } else {
+      const __nv_bfloat16 h = __float2bfloat16_rn(f);
+      r = __bfloat162float(h);
+      hb = __bfloat16_as_ushort(h);
+    }
+    s += r;
+    qq = fmaf(r, r, qq);
+    const uint32_t dst = sbuf_addr + prow * 128u + (((chunk ^ (prow & 7u)) << 4) | col_byte);
+    asm volatile("st.shared.b16 [%0], %1;" ::"r"(dst), "h"(hb) : "memory");
+  }
+}
+
+template <bool H>
+__device__ __forceinline__ void stage_row32(const uint32_t* v, float alpha, const float* bv, uint32_t row_addr, int half,
+                                            int row) {
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    float f[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) f[i] = fmaf(__uint_as_float(v[g * 8 + i]), alpha, bv[g * 8 + i]);
+    const bf16x8 pk = H ? pack8_half(f) : pack8(f);
+    const uint32_t dst = row_addr + (uint32_t)(((half * 4 + g) ^ (row & 7)) << 4);   // SWIZZLE_128B
+    const uint4 u = *reinterpret_cast<const uint4*>(&pk);
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(u.x), "r"(u.y), "r"(u.z), "r"(u.w)
+                 : "memory");
+  }
+}
+
+template <bool H>
+__device__ __forceinline__ void column_pair_sums(uint32_t sbuf_addr, int r8, int cp, float& s, float& qq) {
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int r = r8 * 16 + i;
+    const uint32_t a = sbuf_addr + (uint32_t)r * 128u + (uint32_t)((((cp >> 2) ^ (r & 7)) << 4) | ((cp & 3) << 2));
+    uint32_t wv;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(wv) : "r"(a));
+    float x0, x1;
+    decode2_fmt(wv, H, x0, x1);
+    s += x0 + x1;
+    qq = fmaf(x0, x0, qq);
+    qq = fmaf(x1, x1, qq);
+  }
+}
+
 // TM ("transposed accumulator", Cout tile of 128 with two row boxes): the MMA takes the WEIGHT tile as
 // its A operand (M = 128 channels) and the 256-pixel activation tile as its B operand (N = 256), so a
 // k-block is 4 instructions of N = 256 instead of 8 of N = 128 — measured, an N = 128 tcgen05.mma costs
 // ~98 clocks against its 64-clock floor while N = 256 runs at its 128-clock floor.  The accumulator is
 // then [channel lane][pixel column]; the epilogue transposes it through the swizzled staging panels
 // with 16-bit shared-memory stores, and the GroupNorm statistics become per-thread sums.
-template <int BN, int STAGES, int MT, int KS, bool TM>
+template <int BN, int STAGES, int MT, int KS, bool TM, bool F16>
 __global__ void __launch_bounds__(P_THREADS, 1)
 tapgemm_persist_kernel(const __grid_constant__ TapGemmParams p, const __grid_constant__ CUtensorMap tmA0,
                        const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
@@ -383,17 +442,7 @@ tapgemm_persist_kernel(const __grid_constant__ TapGemmParams p, const __grid_con
           float s = 0.f, qq = 0.f;
           const uint32_t col_byte = (cc & 7u) * 2u;
           const uint32_t chunk = cc >> 3;
-#pragma unroll
-          for (int i = 0; i < 64; ++i) {
-            const uint32_t prow = (uint32_t)(half * 64 + i);          // pixel row within the 128-row box
-            const float f = fmaf(__uint_as_float(v[i]), p.alpha, bvs);
-            const __nv_bfloat16 h = __float2bfloat16_rn(f);
-            const float r = __bfloat162float(h);
-            s += r;
-            qq = fmaf(r, r, qq);
-            const uint32_t dst = smem_u32(sbuf) + prow * 128u + (((chunk ^ (prow & 7u)) << 4) | col_byte);
-            asm volatile("st.shared.b16 [%0], %1;" ::"r"(dst), "h"(*reinterpret_cast<const unsigned short*>(&h)) : "memory");
-          }
+          tm_stage_column<F16>(v, p.alpha, bvs, smem_u32(sbuf), half, chunk, col_byte, s, qq);
           fence_proxy_async_smem();
           mbar_arrive(&pfull_bar[sb]);
           if (p.stats != nullptr) {
@@ -486,18 +535,7 @@ tapgemm_persist_kernel(const __grid_constant__ TapGemmParams p, const __grid_con
           for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(acc[i] + __uint_as_float(v[i]));
         }
         const uint32_t row_addr = smem_u32(sbuf) + (uint32_t)row * 128u;
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          float f[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) f[i] = fmaf(__uint_as_float(v[g * 8 + i]), p.alpha, bv[g * 8 + i]);
-          const bf16x8 pk = pack8(f);
-          const uint32_t dst = row_addr + (uint32_t)(((half * 4 + g) ^ (row & 7)) << 4);   // SWIZZLE_128B
-          const uint4 u = *reinterpret_cast<const uint4*>(&pk);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(u.x), "r"(u.y), "r"(u.z),
-                       "r"(u.w)
-                       : "memory");
-        }
+        stage_row32<F16>(v, p.alpha, bv, row_addr, half, row);
         fence_proxy_async_smem();
         mbar_arrive(&pfull_bar[sb]);
         if (p.stats != nullptr && p.bb > 8) {
@@ -514,8 +552,9 @@ tapgemm_persist_kernel(const __grid_constant__ TapGemmParams p, const __grid_con
                                  (uint32_t)((((ch >> 1) ^ (r & 7)) << 4) | ((ch & 1) << 3));
               uint32_t w0, w1;
               asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(w0), "=r"(w1) : "r"(a));
-              const float x0 = __uint_as_float(w0 << 16), x1 = __uint_as_float(w0 & 0xffff0000u);
-              const float x2 = __uint_as_float(w1 << 16), x3 = __uint_as_float(w1 & 0xffff0000u);
+              float x0, x1, x2, x3;
+              decode2_fmt(w0, F16, x0, x1);
+              decode2_fmt(w1, F16, x2, x3);
               s += (x0 + x1) + (x2 + x3);
               qq = fmaf(x0, x0, qq); qq = fmaf(x1, x1, qq); qq = fmaf(x2, x2, qq); qq = fmaf(x3, x3, qq);
             }
@@ -536,18 +575,7 @@ tapgemm_persist_kernel(const __grid_constant__ TapGemmParams p, const __grid_con
           }
           // column sums over the staged bf16 panel: thread = (16-row sub-block, column pair)
           float s = 0.f, qq = 0.f;
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const int r = r8 * 16 + i;
-            const uint32_t a = smem_u32(sbuf) + (uint32_t)r * 128u +
-                               (uint32_t)((((cp >> 2) ^ (r & 7)) << 4) | ((cp & 3) << 2));
-            uint32_t wv;
-            asm volatile("ld.shared.b32 %0, [%1];" : "=r"(wv) : "r"(a));
-            const float x0 = __uint_as_float(wv << 16), x1 = __uint_as_float(wv & 0xffff0000u);
-            s += x0 + x1;
-            qq = fmaf(x0, x0, qq);
-            qq = fmaf(x1, x1, qq);
-          }
+          column_pair_sums<F16>(smem_u32(sbuf), r8, cp, s, qq);
           s += __shfl_xor_sync(0xffffffffu, s, 1);
           qq += __shfl_xor_sync(0xffffffffu, qq, 1);
           if ((cp & 1) == 0) red[sb * 128 + r8 * 16 + (cp >> 1)] = make_float2(s, qq);
@@ -666,12 +694,12 @@ bool tapgemm_persist_eligible(const its_conv_desc* d, const TapGemmParams& p) {
   return true;
 }
 
-template <int BN, int STAGES, int MT, int KS, bool TM = false>
-static int launch_persist(const TapGemmParams& p, const CUtensorMap* tmA, const CUtensorMap& tmB,
-                          const CUtensorMap& tmOut, cudaStream_t stream) {
+template <int BN, int STAGES, int MT, int KS, bool TM, bool F16>
+static int launch_persist_fmt(const TapGemmParams& p, const CUtensorMap* tmA, const CUtensorMap& tmB,
+                              const CUtensorMap& tmOut, cudaStream_t stream) {
   using L = PersistSmem<BN, STAGES, MT, KS, TM>;
   static_assert(L::TOTAL <= 227 * 1024, "shared memory budget");
-  auto kern = tapgemm_persist_kernel<BN, STAGES, MT, KS, TM>;
+  auto kern = tapgemm_persist_kernel<BN, STAGES, MT, KS, TM, F16>;
   static bool configured = false;
   if (!configured) {
     ITS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
@@ -691,6 +719,15 @@ static int launch_persist(const TapGemmParams& p, const CUtensorMap* tmA, const 
   cfg.numAttrs = pdl_enabled(1) ? 1 : 0;
   ITS_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, p, tmA[0], tmA[1], tmA[2], tmB, tmOut));
   return ITS_OK;
+}
+
+// the 16-bit output format (bf16 / IEEE fp16) is a compile-time parameter of the kernel: a run-time test inside
+// the unrolled epilogue loops cost 1.3-1.8 % of a config-A pass (measured)
+template <int BN, int STAGES, int MT, int KS, bool TM = false>
+static int launch_persist(const TapGemmParams& p, const CUtensorMap* tmA, const CUtensorMap& tmB,
+                          const CUtensorMap& tmOut, cudaStream_t stream) {
+  if (p.out_fp16) return launch_persist_fmt<BN, STAGES, MT, KS, TM, true>(p, tmA, tmB, tmOut, stream);
+  return launch_persist_fmt<BN, STAGES, MT, KS, TM, false>(p, tmA, tmB, tmOut, stream);
 }
 
 int tapgemm_launch_persist(const its_conv_desc* d, const TapGemmParams& p, cudaStream_t stream) {

@@ -22,8 +22,11 @@ struct GnArgs {
   const float* beta;
   float* partials;
   int C0, C1, C, HW, groups, chunks, silu, out_fp16;
+  int src0_fp16, src1_fp16;     // 16-bit format of the sources
   float eps;
 };
+
+__device__ __forceinline__ bool gn_half(const GnArgs& a, int c0) { return (c0 < a.C0 ? a.src0_fp16 : a.src1_fp16) != 0; }
 
 __device__ __forceinline__ bf16x8 gn_load(const GnArgs& a, long long pix, int c0) {
   // pix = global pixel index (image*HW + p); c0 = first channel of the vector
@@ -49,7 +52,7 @@ __global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(const GnArgs a) {
   if (pl < prow) {
     for (int p = p0 + pl; p < p1; p += prow) {
       float f[8];
-      unpack8(gn_load(a, (long long)img * a.HW + p, cv * 8), f);
+      unpack8_fmt(gn_load(a, (long long)img * a.HW + p, cv * 8), f, gn_half(a, cv * 8));
 #pragma unroll
       for (int i = 0; i < 8; ++i) { sum[i] += f[i]; sq[i] = fmaf(f[i], f[i], sq[i]); }
     }
@@ -121,7 +124,7 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const GnArgs a) {
   for (int p = p0 + pl; p < p1; p += prow) {
     const long long pix = (long long)img * a.HW + p;
     float f[8];
-    unpack8(gn_load(a, pix, cv * 8), f);
+    unpack8_fmt(gn_load(a, pix, cv * 8), f, gn_half(a, cv * 8));
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       float v = fmaf(f[i], scale[i], shift[i]);
@@ -172,7 +175,7 @@ __global__ void __launch_bounds__(GN_THREADS) gn_cluster_kernel(const GnArgs a) 
         if (p < p1) {
           if (CACHE) *reinterpret_cast<bf16x8*>(cache + (long long)(p - p0) * a.C + cv * 8) = raw[u];
           float f[8];
-          unpack8(raw[u], f);
+          unpack8_fmt(raw[u], f, gn_half(a, cv * 8));
 #pragma unroll
           for (int i = 0; i < 8; ++i) { sum[i] += f[i]; sq[i] = fmaf(f[i], f[i], sq[i]); }
         }
@@ -228,9 +231,9 @@ __global__ void __launch_bounds__(GN_THREADS) gn_cluster_kernel(const GnArgs a) 
     const long long pix = (long long)img * a.HW + p;
     float f[8];
     if (CACHE)
-      unpack8(*reinterpret_cast<const bf16x8*>(cache + (long long)(p - p0) * a.C + cv * 8), f);
+      unpack8_fmt(*reinterpret_cast<const bf16x8*>(cache + (long long)(p - p0) * a.C + cv * 8), f, gn_half(a, cv * 8));
     else
-      unpack8(gn_load(a, pix, cv * 8), f);
+      unpack8_fmt(gn_load(a, pix, cv * 8), f, gn_half(a, cv * 8));
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const float v = fmaf(f[i], scale[i], shift[i]);
@@ -256,9 +259,12 @@ struct GnStatArgs {
   const float2* st0;
   const float2* st1;
   int C0, C1, C, HW, groups, parts0, parts1, silu, chunks, out_fp16;
+  int src0_fp16, src1_fp16;     // 16-bit format of the sources (raw feature maps: bf16 unless the fp16 residual stream is on)
   float eps;
 };
 
+// FMT: 16-bit format of the sources at compile time — 0 = bf16, 1 = IEEE fp16, 2 = per source (run-time flags)
+template <int FMT>
 __global__ void __launch_bounds__(GN_THREADS, 4) gn_apply_stats_kernel(const GnStatArgs a) {
   __shared__ float s_mean[64], s_rstd[64];
   const int tid = threadIdx.x;
@@ -275,6 +281,7 @@ __global__ void __launch_bounds__(GN_THREADS, 4) gn_apply_stats_kernel(const GnS
   const bool from0 = cv * 8 < a.C0;
   const __nv_bfloat16* sp = from0 ? a.src0 + cv * 8 : a.src1 + (cv * 8 - a.C0);
   const int spitch = from0 ? a.C0 : a.C1;
+  const bool src_half = FMT == 2 ? ((from0 ? a.src0_fp16 : a.src1_fp16) != 0) : (FMT == 1);
   constexpr int U = 4;                   // independent 16-byte loads in flight per thread
   pdl_prologue();
   // first batch of activations and the affine parameters are requested before the
@@ -348,7 +355,7 @@ __global__ void __launch_bounds__(GN_THREADS, 4) gn_apply_stats_kernel(const GnS
       const int p = pb + u * prow;
       if (p < p1) {
         float f[8];
-        unpack8(raw[u], f);
+        unpack8_fmt(raw[u], f, src_half);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const float v = fmaf(f[i], scale[i], shift[i]);
@@ -413,7 +420,7 @@ extern "C" int its_group_norm(void* out, const void* src0, int32_t C0, const voi
   a.out = static_cast<__nv_bfloat16*>(out);
   a.gamma = gamma; a.beta = beta; a.partials = partials;
   a.C0 = C0; a.C1 = C1; a.C = C; a.HW = HW; a.groups = groups; a.chunks = chunks; a.silu = silu;
-  a.out_fp16 = out_fp16;
+  a.out_fp16 = out_fp16 & 1; a.src0_fp16 = (out_fp16 >> 1) & 1; a.src1_fp16 = (out_fp16 >> 2) & 1;
   a.eps = eps;
   if (chunks <= 8) {
     // one launch: cluster of `chunks` CTAs per image
@@ -454,7 +461,8 @@ extern "C" int its_group_norm_apply(void* out, const void* src0, int32_t C0, con
   a.st0 = reinterpret_cast<const float2*>(stats0);
   a.st1 = reinterpret_cast<const float2*>(stats1);
   a.C0 = C0; a.C1 = C1; a.C = C; a.HW = HW; a.groups = groups; a.parts0 = parts0; a.parts1 = parts1;
-  a.silu = silu; a.eps = eps; a.out_fp16 = out_fp16;
+  // out_fp16 carries three flags: bit 0 = output format, bit 1 / bit 2 = source 0 / source 1 hold IEEE fp16
+  a.silu = silu; a.eps = eps; a.out_fp16 = out_fp16 & 1; a.src0_fp16 = (out_fp16 >> 1) & 1; a.src1_fp16 = (out_fp16 >> 2) & 1;
   // one wave: at most 4 CTAs per SM are resident (launch bounds), and every CTA repeats the
   // statistics prologue of its image, so the grid is sized to fit the machine exactly once
   long long chunks = ((long long)HW * C * 2 + 32767) / 32768;
@@ -464,7 +472,14 @@ extern "C" int its_group_norm_apply(void* out, const void* src0, int32_t C0, con
   if (chunks > HW) chunks = HW;
   a.chunks = (int)chunks;
   dim3 grid((unsigned)chunks, (unsigned)n_img);
-  ITS_LAUNCH(gn_apply_stats_kernel, dim3(grid), dim3(GN_THREADS), 0, as_stream(stream), a);
+  const int s1 = (C1 > 0) ? a.src1_fp16 : a.src0_fp16;
+  if (a.src0_fp16 == 0 && s1 == 0) {
+    ITS_LAUNCH(gn_apply_stats_kernel<0>, dim3(grid), dim3(GN_THREADS), 0, as_stream(stream), a);
+  } else if (a.src0_fp16 == 1 && s1 == 1) {
+    ITS_LAUNCH(gn_apply_stats_kernel<1>, dim3(grid), dim3(GN_THREADS), 0, as_stream(stream), a);
+  } else {
+    ITS_LAUNCH(gn_apply_stats_kernel<2>, dim3(grid), dim3(GN_THREADS), 0, as_stream(stream), a);
+  }
   ITS_CHECK_LAUNCH();
   return ITS_OK;
 }

@@ -103,6 +103,29 @@ __device__ __forceinline__ bf16x8 pack8_half(const float* f) {
   return p;
 }
 
+// 8 IEEE halves -> 8 floats, and the format-dispatching pair used where a tensor may hold either 16-bit format
+__device__ __forceinline__ void unpack8_half(const bf16x8& p, float* f) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = __half22float2(*reinterpret_cast<const __half2*>(&p.v[i]));
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ void unpack8_fmt(const bf16x8& p, float* f, bool half) {
+  if (half) unpack8_half(p, f); else unpack8(p, f);
+}
+__device__ __forceinline__ bf16x8 pack8_fmt(const float* f, bool half) { return half ? pack8_half(f) : pack8(f); }
+// two packed 16-bit values of either format -> floats
+__device__ __forceinline__ void decode2_fmt(uint32_t w, bool half, float& a, float& b) {
+  if (half) {
+    const float2 t = __half22float2(*reinterpret_cast<const __half2*>(&w));
+    a = t.x; b = t.y;
+  } else {
+    a = __uint_as_float(w << 16); b = __uint_as_float(w & 0xffff0000u);
+  }
+}
+
 // Philox4x32-10 (Salmon et al., SC'11), the counter-based generator the DDPM
 // step and the candidate generators share.  The host/oracle restatement is
 // oracle/philox.py.

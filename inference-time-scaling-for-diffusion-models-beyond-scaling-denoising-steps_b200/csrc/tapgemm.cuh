@@ -46,6 +46,8 @@ struct TapGemmParams {
   long long* dbg;            // optional per-CTA clock stamps (diagnostics)
   float* stats;              // GroupNorm partial sums [B][stats_parts][Cout/4][2] or null (persistent kernel)
   int stats_parts;
+  int out_fp16;              // 16-bit output format: 0 = bf16, 1 = IEEE fp16
+  int res_fp16;              // format of the residual tensor read by the non-folded epilogues
   // M tiling: a 128-row tile is a (bb images) x (bh rows) x (bw cols) box
   int bw, bh, bb, tiles_x, tiles_y, tiles_b;
 };

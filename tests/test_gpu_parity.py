@@ -157,6 +157,50 @@ def test_sampler_injected_noise_vs_reference(cuda_dev, name, graph):
     assert abs(V.SelfSupervisedVerifier().score(d) - float(g["score_self_supervised"])) <= SCORE_TOL
 
 
+@pytest.mark.parametrize("name", ["u_small_T20", "c_small_T20"])
+def test_fp16_residual_stream_mode_is_more_accurate(cuda_dev, name):
+    """Opt-in `model.residual_fp16 = True`: raw feature maps in IEEE fp16 instead of bf16 (the bf16 residual
+    stream is the dominant error term).  Same fixtures, smaller error; the default mode
+    is untouched."""
+    cfg = cases.SAMPLER_CASES[name]
+    x_T, noise, labels = cases.sampler_inputs(cfg)
+    ref = torch.from_numpy(golden("smp_" + name)["x0"])
+    errs = {}
+    for mode in (False, True):
+        net, _ = build_shell(cfg, cuda_dev)
+        net.residual_fp16 = mode
+        if cfg["kind"] == "uncond":
+            from its_b200.Diffusion import GaussianDiffusionSampler
+            smp = GaussianDiffusionSampler(net, cfg["beta_1"], cfg["beta_T"], cfg["T"]).to(cuda_dev)
+            smp.print_steps = False
+            x0 = smp(x_T.to(cuda_dev), noise=noise.to(cuda_dev))
+        else:
+            from its_b200.DiffusionFreeGuidence import GaussianDiffusionSampler
+            smp = GaussianDiffusionSampler(net, cfg["beta_1"], cfg["beta_T"], cfg["T"], w=cfg["w"]).to(cuda_dev)
+            smp.print_steps = False
+            x0 = smp(x_T.to(cuda_dev), labels.to(cuda_dev), noise=noise.to(cuda_dev))
+        plan = next(iter(net._plans.values()))
+        assert (plan.res_dtype == torch.float16) == mode
+        errs[mode] = (x0.cpu() - ref).abs().max().item()
+    print(name, "max abs: bf16 residual stream %.5f, fp16 residual stream %.5f" % (errs[False], errs[True]))
+    assert errs[False] <= 2e-2 and errs[True] <= 8e-3
+    assert errs[True] < 0.7 * errs[False]
+
+
+def test_fp16_residual_stream_forward_full_size(cuda_dev):
+    cfg = cases.FORWARD_CASES["u_A"]
+    x, t, labels = cases.forward_inputs(cfg)
+    ref = torch.from_numpy(golden("fwd_u_A")["eps"])
+    e = {}
+    for mode in (False, True):
+        net, _ = build_shell(cfg, cuda_dev)
+        net.residual_fp16 = mode
+        eps = net(x.to(cuda_dev), t.to(cuda_dev)).cpu()
+        e[mode] = rms_err(eps, ref)
+    print("config A eps rms error: bf16 residual stream %.2e, fp16 %.2e" % (e[False], e[True]))
+    assert e[True] < 4e-3 and e[True] < 0.6 * e[False]
+
+
 def test_p_mean_variance_seam(cuda_dev):
     """The public seam the reference's own external loop drives (Diffusion/Train.py:68-77)."""
     cfg = cases.SAMPLER_CASES["u_small_T20"]
