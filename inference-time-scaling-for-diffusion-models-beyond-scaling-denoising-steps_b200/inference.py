@@ -168,6 +168,11 @@ def create_and_load_model(config: Dict[str, Any], device) -> nn.Module:
             print(f"Warning: Unexpected keys: {list(unexpected)}")
         if missing:
             print(f"Warning: Missing keys: {list(missing)}")
+    # Raw feature maps in fp16 instead of bf16 (5x smaller error) need bounded activations:
+    # `residual_fp16: auto` (default) turns it on for loaded checkpoints (trained weights) and leaves random
+    # initialisations, whose state can grow past fp16's range, on bf16; true / false force it.
+    mode = config.get("residual_fp16", "auto")
+    model.residual_fp16 = bool(path) if mode == "auto" else bool(mode)
     return model.eval()
 
 

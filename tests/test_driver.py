@@ -74,6 +74,9 @@ def test_table_checkpoint_of_another_T_extends_the_conditional_net(tmp_path):
     assert torch.equal(m.cond_embedding.condEmbedding[1].weight, src.cond_embedding.condEmbedding[1].weight)
     smp = I.create_sampler(m, cfg, "cpu")
     assert smp.w == 1.8 and smp.T == 900
+    assert m.residual_fp16 is True                       # auto: a checkpoint was loaded
+    assert I.create_and_load_model(dict(cfg, checkpoint_path=None), "cpu").residual_fp16 is False
+    assert I.create_and_load_model(dict(cfg, checkpoint_path=str(p), residual_fp16=False), "cpu").residual_fp16 is False
 
 
 class _FakeFID:
