@@ -112,56 +112,143 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------ CPU arm --
-def cpu_reference_sample(batch: int, n_steps: int, seed: int = 0):
-    """The reference's CPU path (oracle port, all host threads): `n_steps` of the
-    T=1000 ancestral loop for config A at `batch` images + the verifier; returns
-    (seconds, extrapolated candidate images/s for the full T=1000 trajectory)."""
-    from oracle import ddpm_oracle as O
-    from its_b200.Diffusion import UNet
-    torch.manual_seed(seed)
-    net = UNet(**CFG_A)                          # same constructor/initialisers as the reference
-    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
-    sched = O.schedule(BETA_1, BETA_T, CFG_A["T"])
-    x = torch.randn(batch, 3, 32, 32)
-    t0 = time.perf_counter()
-    with torch.no_grad(), contextlib.redirect_stdout(io.StringIO()):
-        x0 = O.sample(sd, sched, x, lambda s: torch.randn(batch, 3, 32, 32), t_start=CFG_A["T"] - 1
-                      if n_steps >= CFG_A["T"] else None) if n_steps >= CFG_A["T"] else _partial(O, sd, sched, x, n_steps)
-        O.oracle_verifier_score(torch.clip(x0, -1, 1))
-    dt = time.perf_counter() - t0
-    full = dt * CFG_A["T"] / min(n_steps, CFG_A["T"])
-    return dt, batch / full
+def _host_threads():
+    """Threads the CPU arm may use: the cores this process is allowed on.  torchrun exports OMP_NUM_THREADS=1
+    to its workers, which is what starved the round-1 reference arm at N > 1: set the count explicitly."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except (AttributeError, OSError):
+        n = os.cpu_count() or 1
+    torch.set_num_threads(max(1, n))
+    return torch.get_num_threads()
 
 
-def _partial(O, sd, sched, x, n_steps):
-    T = CFG_A["T"]
-    for time_step in range(T - 1, T - 1 - n_steps, -1):
-        t = torch.full((x.shape[0],), time_step, dtype=torch.long)
-        mean, var, _ = O.p_mean_variance(sd, sched, x, t)
-        x = mean + torch.sqrt(var) * torch.randn_like(x)
-    return x
+def _load_reference():
+    """The reference's own modules (Diffusion/Diffusion.py, Diffusion/Model.py, search/verifier.py) loaded by file
+    path when a checkout is reachable ($ITS_REF_DIR, then /root/reference — the build container only; the GPU
+    box has none).  Returns None when absent: the oracle port (oracle/ddpm_oracle.py) is timed instead."""
+    import importlib.util
+    for root in (os.environ.get("ITS_REF_DIR"), "/root/reference"):
+        if not root or not os.path.exists(os.path.join(root, "Diffusion", "Diffusion.py")):
+            continue
+        mods = {}
+        try:
+            for name, rel in (("diffusion", "Diffusion/Diffusion.py"), ("model", "Diffusion/Model.py"),
+                              ("verifier", "search/verifier.py")):
+                spec = importlib.util.spec_from_file_location("bench_ref_" + name, os.path.join(root, rel))
+                mod = importlib.util.module_from_spec(spec)
+                with contextlib.redirect_stdout(io.StringIO()):
+                    spec.loader.exec_module(mod)
+                mods[name] = mod
+        except Exception:       # noqa: BLE001 — a broken checkout must not take the bench line down
+            continue
+        return mods
+    return None
+
+
+class CpuArm:
+    """The reference's CPU path for workload A: `n_steps` of the T = 1000 ancestral loop over `batch` candidate
+    images (Diffusion.py:84-102 through its public seam p_mean_variance) + OracleVerifier.score (verifier.py:62),
+    fp32, every host thread.  The loop is step-homogeneous, so candidate images/s for the full trajectory is
+    batch / (seconds * T / n_steps)."""
+
+    def __init__(self, seed: int = 0):
+        self.T = CFG_A["T"]
+        self.threads = _host_threads()
+        self.ref = _load_reference()
+        torch.manual_seed(seed)
+        if self.ref is not None:
+            self.kind = "reference"
+            net = self.ref["model"].UNet(**CFG_A).eval()
+            self.smp = self.ref["diffusion"].GaussianDiffusionSampler(net, BETA_1, BETA_T, self.T)
+            self.ver = self.ref["verifier"].OracleVerifier()
+        else:
+            from oracle import ddpm_oracle as O
+            from its_b200.Diffusion import UNet
+            self.kind = "port"
+            self.O = O
+            net = UNet(**CFG_A)                      # same constructor / initialisers as the reference
+            self.sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+            self.sched = O.schedule(BETA_1, BETA_T, self.T)
+
+    def sample(self, batch: int, n_steps: int):
+        """(seconds, extrapolated candidate images/s)."""
+        T = self.T
+        n_steps = max(1, min(n_steps, T))
+        x = torch.randn(batch, 3, 32, 32)
+        t0 = time.perf_counter()
+        with torch.no_grad(), contextlib.redirect_stdout(io.StringIO()):
+            for time_step in range(T - 1, T - 1 - n_steps, -1):
+                t = torch.full((batch,), time_step, dtype=torch.long)
+                if self.ref is not None:
+                    mean, var = self.smp.p_mean_variance(x_t=x, t=t)
+                else:
+                    mean, var, _ = self.O.p_mean_variance(self.sd, self.sched, x, t)
+                x = mean + torch.sqrt(var) * torch.randn_like(x)
+            x0 = torch.clip(x, -1, 1)
+            if self.ref is not None:
+                self.ver.score(x0)
+            else:
+                self.O.oracle_verifier_score(x0)
+        dt = time.perf_counter() - t0
+        return dt, batch / (dt * T / n_steps)
+
+    def describe(self, batch, n_steps, dt):
+        what = ("the reference's own modules (Diffusion/Diffusion.py + Model.py + search/verifier.py, loaded by path)"
+                if self.ref is not None else "oracle port of Diffusion.py:84-102 + verifier.py:62 (oracle/ddpm_oracle.py)")
+        return (f"{what}, config A, {batch} candidate images per sample, {n_steps} of {self.T} denoising steps "
+                f"({dt:.1f} s) + verifier, extrapolated x{self.T / n_steps:.1f} (the loop is step-homogeneous); "
+                f"{self.threads} threads on {os.cpu_count()} logical CPUs")
+
+
+def cpu_sample_for_budget(arm: CpuArm, batch: int, n_samples: int, budget_s: float, forced: int = 0):
+    """(candidates per CPU sample, denoising steps per sample) so that `n_samples` samples fit `budget_s`.
+    The population is the workload's own; it is only cut (never below 8 images) when one single denoising
+    step of the whole population would already overrun the budget on this host."""
+    if forced > 0:
+        return batch, forced
+    arm.sample(min(batch, 8), 1)                      # page-in / thread pool warm-up
+    per = budget_s / max(n_samples, 1)
+    while True:
+        dt, _ = arm.sample(batch, 1)
+        if dt <= per or batch <= 8:
+            break
+        batch = max(8, batch // 2)
+    return batch, max(1, min(arm.T, int(per / max(dt, 1e-3))))
 
 
 def run_reference(args):
+    """`--impl reference`: the CPU arm on the same config / metric / unit as ours.  Under torchrun only rank 0
+    works; every other rank exits 0 at once (no process group is created)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = torch.get_num_threads()
-    batch, n_steps = 8, args.ref_steps
+    if args.workload != "A":
+        print(json.dumps({"impl": "reference", "unavailable": "the CPU arm is defined for workload A (BASELINE.json configs[1])"}))
+        return
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    arm = CpuArm()
+    total = args.warmup + args.steps
+    # the workload's own per-step population, T sampled
+    batch, n_steps = cpu_sample_for_budget(arm, args.candidates, total, args.ref_budget, args.ref_steps)
     vals, secs = [], []
-    for i in range(args.warmup + args.steps):
-        dt, v = cpu_reference_sample(batch, n_steps, seed=i)
+    for i in range(total):
+        dt, v = arm.sample(batch, n_steps)
         if i >= args.warmup:
             vals.append(v); secs.append(dt)
     value = statistics.mean(vals)
-    sample = (f"oracle port of Diffusion.py:84-102 + verifier.py:62, config A, batch {batch}, {n_steps} of 1000 "
-              f"denoising steps per bench step, extrapolated x{1000 // n_steps} (loop is step-homogeneous)")
+    sample = arm.describe(batch, n_steps, statistics.mean(secs))
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * statistics.mean(secs), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, 1),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "config": workload_config(args, world),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": arm.threads, "logical_cpus": os.cpu_count(),
+                         "kind": arm.kind, "sample": sample},
+        "reference_run": {"what": "GPU versus CPU: one host, all threads, no GPU", "candidates_per_sample": batch,
+                          "denoising_steps_per_sample": n_steps, "of_T": arm.T, "extrapolation": arm.T / n_steps,
+                          "threads": arm.threads, "logical_cpus": os.cpu_count(),
+                          "omp_num_threads_env": os.environ.get("OMP_NUM_THREADS")},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -293,10 +380,11 @@ def run_ours(args):
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu_baseline and args.workload == "A":
-            cores = torch.get_num_threads()
-            dt_cpu, v_cpu = cpu_reference_sample(8, args.ref_steps)
-            cpu = {"value": v_cpu, "unit": UNIT, "cores": cores, "kind": "port",
-                   "sample": f"oracle port, config A, batch 8, {args.ref_steps} of 1000 steps ({dt_cpu:.1f} s), extrapolated"}
+            arm = CpuArm()
+            b_cpu, n_cpu = cpu_sample_for_budget(arm, n_local, 1, args.cpu_budget, args.ref_steps)
+            dt_cpu, v_cpu = arm.sample(b_cpu, n_cpu)
+            cpu = {"value": v_cpu, "unit": UNIT, "cores": arm.threads, "logical_cpus": os.cpu_count(), "kind": arm.kind,
+                   "sample": arm.describe(b_cpu, n_cpu, dt_cpu)}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -417,7 +505,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="A", choices=sorted(WORKLOADS), help="A = BASELINE.json configs[1] (default)")
     ap.add_argument("--candidates", type=int, default=None, help="candidates per GPU (weak scaling); default per workload")
-    ap.add_argument("--ref-steps", type=int, default=100, help="denoising steps per CPU sample (of T=1000)")
+    ap.add_argument("--ref-steps", type=int, default=0,
+                    help="denoising steps per CPU sample (of T=1000); 0 = sized from the time budget")
+    ap.add_argument("--ref-budget", type=float, default=150.0, help="seconds for the whole --impl reference run")
+    ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds for the cpu_baseline leg of our arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.candidates is None:

@@ -38,6 +38,23 @@ SEARCH_CASES = {
 }
 
 
+# Full-length / full-width fixtures (tests/golden/make_golden_long.py, make_golden_long2.py)
+LONG_CASES = {
+    "u_A_T1000": dict(U_A, T=1000, beta_1=1e-4, beta_T=0.02, B=2, input_seed=601, noise_seed=602, weight_seed=61,
+                      keep_at=(900, 500, 100)),
+    "c_C_T1000": dict(C_C, T=1000, beta_1=1e-4, beta_T=0.02, w=1.8, B=2, input_seed=611, noise_seed=612,
+                      weight_seed=62, keep_at=(900, 500, 100)),
+    "u_E_T2000": dict(U_E, T=2000, beta_1=1e-4, beta_T=0.02, B=1, input_seed=621, noise_seed=622, weight_seed=63,
+                      keep_at=(1800, 1000, 200)),
+    # the reference's own initialisers under torch.manual_seed(init_seed) (no synthetic weights)
+    "u_A_refinit": dict(U_A, T=1000, beta_1=1e-4, beta_T=0.02, B=2, input_seed=631, noise_seed=632, init_seed=0,
+                        keep_at=(900, 500, 100)),
+    # random search at config A's real width: 64 single-image candidates, T = 50
+    "u_A_search64": dict(U_A, T=50, beta_1=1e-4, beta_T=0.02, weight_seed=64, noise_shape=[1, 3, 32, 32],
+                         noise_seed=641, cand_seed=642, n_candidates=64, verifier="oracle"),
+}
+
+
 def _randn(seed, shape):
     return torch.from_numpy(np.random.default_rng(seed).standard_normal(shape).astype(np.float32))
 
@@ -66,6 +83,11 @@ def sampler_inputs(cfg):
 
 def search_noise(cfg):
     return _randn(cfg["noise_seed"], (cfg["T"],) + tuple(cfg["noise_shape"]))
+
+
+def search_candidates(cfg):
+    """Candidate noises [n_candidates, *noise_shape] from a numpy seed (injected into the searches)."""
+    return _randn(cfg["cand_seed"], (cfg["n_candidates"],) + tuple(cfg["noise_shape"]))
 
 
 def search_labels(cfg):
