@@ -291,18 +291,7 @@ def run_ours(args):
 
     wl = WORKLOADS[args.workload]
     T, img = wl["T"], wl["img"]
-    torch.manual_seed(0)
-    labels = None
-    if wl["cond"]:
-        from its_b200.DiffusionFreeGuidence import GaussianDiffusionSampler, UNet
-        net = UNet(T=T, num_labels=10, ch=128, ch_mult=[1, 2, 3, 4], num_res_blocks=2, dropout=0.15).to(dev).eval()
-        smp = GaussianDiffusionSampler(net, BETA_1, BETA_T, T, w=wl["w"]).to(dev)
-        labels = torch.tensor([3], dtype=torch.int64, device=dev)     # one class per search (noise_shape batch = 1)
-    else:
-        from its_b200.Diffusion import GaussianDiffusionSampler, UNet
-        net = UNet(**dict(CFG_A, T=T, attn=wl["attn"])).to(dev).eval()
-        smp = GaussianDiffusionSampler(net, BETA_1, BETA_T, T).to(dev)
-    smp.print_steps = False
+    net, smp, labels = build_workload(args.workload, dev)
     n_local, n_total = args.candidates, args.candidates * world
     shape = (1, 3, img, img)
     den = S.make_denoise_fn(smp, labels, max_images=args.candidates, seed=1234)
@@ -375,6 +364,10 @@ def run_ours(args):
     if args.workload == "A" and n_local == 64:
         roof.update(ncu_traffic("tapgemm"))
     hbm = profile_hbm_kernels(plan, smp, dev, pk, n_local, img, wl)
+    # BASELINE.json configs[2] and configs[4] on the same record: one bounded search each (N = 1 default run only)
+    extra = None
+    if world == 1 and args.workload == "A" and not args.no_extra_workloads:
+        extra = {k: run_extra_workload(k, dev, pk) for k in ("C", "E")}
 
     line = None
     if rank == 0:
@@ -394,11 +387,72 @@ def run_ours(args):
             "clocks": clocks.summary(),
             "best_score": best_score,
         }
+        if extra is not None:
+            line["workloads"] = extra
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     return line
+
+
+def build_workload(key, dev):
+    """(net, sampler, labels) of a workload with random-init weights of that architecture."""
+    wl = WORKLOADS[key]
+    T = wl["T"]
+    torch.manual_seed(0)
+    labels = None
+    if wl["cond"]:
+        from its_b200.DiffusionFreeGuidence import GaussianDiffusionSampler, UNet
+        net = UNet(T=T, num_labels=10, ch=128, ch_mult=[1, 2, 3, 4], num_res_blocks=2, dropout=0.15).to(dev).eval()
+        smp = GaussianDiffusionSampler(net, BETA_1, BETA_T, T, w=wl["w"]).to(dev)
+        labels = torch.tensor([3], dtype=torch.int64, device=dev)     # one class per search (noise_shape batch = 1)
+    else:
+        from its_b200.Diffusion import GaussianDiffusionSampler, UNet
+        net = UNet(**dict(CFG_A, T=T, attn=wl["attn"])).to(dev).eval()
+        smp = GaussianDiffusionSampler(net, BETA_1, BETA_T, T).to(dev)
+    smp.print_steps = False
+    return net, smp, labels
+
+
+def run_extra_workload(key, dev, pk):
+    """One timed random search of another single-GPU shard of BASELINE.json (C: 32 guided candidates, configs[2];
+    E: 128 candidates of the 64x64 net at T = 2000, configs[4]) so that those configurations are on the driver's
+    record too.  Warm-up = the last steps of a trajectory (plan build, lazy kernel set-up, graph capture), then
+    ONE complete search, device-timed, candidates resident in HBM; plus the tap-GEMM family's roofline."""
+    from its_b200.search import search_algorithm as S
+    from its_b200.search import verifier as V
+    wl = WORKLOADS[key]
+    T, img, n = wl["T"], wl["img"], wl["candidates"]
+    net, smp, labels = build_workload(key, dev)
+    shape = (1, 3, img, img)
+    den = S.make_denoise_fn(smp, labels, max_images=n, seed=1234)
+    ver = V.OracleVerifier()
+    rs = S.RandomSearch(n_candidates=n)
+    resident = S.philox_normal((n,) + shape, 1234, 0, S.TAG_X_T, dev)
+    den.denoise_candidates(resident, 0, t_start=8)                  # warm-up: same plan, same step graph
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    _, best = rs.search(shape, den, ver.score, device=str(dev), verbose=False, candidate_noise=resident, seed=1234)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    value = n / (ms / 1e3)
+    n_net = 2 * n if wl["cond"] else n
+    plan = net.plan(n_net, img, img, n_img_in=n, uniform_t=True)
+    roof = profile_tapgemm(plan, dev, pk)
+    sum_ms = roof.pop("sum_ms")
+    out = {"workload": wl["name"], "unet": wl["unet"], "candidates": n, "T": T, "value": value, "unit": UNIT,
+           "ms_per_search": ms, "searches_timed": 1, "best_score": best,
+           "launches_per_step": smp.last_launches_per_step,
+           "model_flops_frac_of_sustained": value * plan.flops / n * T / (pk["sustained"] * 1e12),
+           "roofline": {k: roof[k] for k in ("bound", "achieved", "peak", "unit", "frac", "launches_per_unet_pass",
+                                             "flops_per_unet_pass")}}
+    out["roofline"]["step_share"] = sum_ms * T / ms
+    del net, smp, plan, den
+    torch.cuda.empty_cache()
+    return out
 
 
 def ncu_traffic(family):
@@ -510,6 +564,8 @@ def main():
     ap.add_argument("--ref-budget", type=float, default=150.0, help="seconds for the whole --impl reference run")
     ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds for the cpu_baseline leg of our arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra-workloads", action="store_true",
+                    help="skip the one-search measurements of workloads C and E appended to the default line")
     args = ap.parse_args()
     if args.candidates is None:
         args.candidates = WORKLOADS[args.workload]["candidates"]

@@ -60,11 +60,16 @@ class UpSample(ParamOnly):
 class AttnBlock(ParamOnly):
     def __init__(self, in_ch):
         super().__init__()
+        # construction and initialisation order follow Model.py:130-144 draw for draw, so that
+        # torch.manual_seed(s) + the constructor yields the reference's own parameters
         self.group_norm = nn.GroupNorm(32, in_ch)
-        for name in ("proj_q", "proj_k", "proj_v", "proj"):
-            conv = nn.Conv2d(in_ch, in_ch, 1, stride=1, padding=0)
-            _xavier(conv, gain=1e-5 if name == "proj" else 1.0)
-            setattr(self, name, conv)
+        self.proj_q = nn.Conv2d(in_ch, in_ch, 1, stride=1, padding=0)
+        self.proj_k = nn.Conv2d(in_ch, in_ch, 1, stride=1, padding=0)
+        self.proj_v = nn.Conv2d(in_ch, in_ch, 1, stride=1, padding=0)
+        self.proj = nn.Conv2d(in_ch, in_ch, 1, stride=1, padding=0)
+        for conv in (self.proj_q, self.proj_k, self.proj_v, self.proj):
+            _xavier(conv)
+        init.xavier_uniform_(self.proj.weight, gain=1e-5)
 
 
 class ResBlock(ParamOnly):
@@ -78,11 +83,13 @@ class ResBlock(ParamOnly):
         self.shortcut = (nn.Conv2d(in_ch, out_ch, 1, stride=1, padding=0) if in_ch != out_ch
                          else nn.Identity())
         self.attn = AttnBlock(out_ch) if attn else nn.Identity()
-        _xavier(self.block1[2])
-        _xavier(self.temb_proj[1])
-        _xavier(self.block2[3], gain=1e-5)
-        if in_ch != out_ch:
-            _xavier(self.shortcut)
+        # Model.py:199-204 re-initialises EVERY Conv2d / Linear below the block in module order — including
+        # the attention block's projections, whose output projection therefore ends up with gain 1, not the
+        # 1e-5 that AttnBlock.initialize had just given it — and then block2's conv with gain 1e-5.
+        for module in self.modules():
+            if isinstance(module, (nn.Conv2d, nn.Linear)):
+                _xavier(module)
+        init.xavier_uniform_(self.block2[-1].weight, gain=1e-5)
 
 
 class UNet(PlannedUNet):
@@ -118,7 +125,7 @@ class UNet(PlannedUNet):
         assert len(skip_chs) == 0
         self.tail = nn.Sequential(nn.GroupNorm(32, cur), Swish(), nn.Conv2d(cur, 3, 3, stride=1, padding=1))
         _xavier(self.head)
-        _xavier(self.tail[2], gain=1e-5)
+        _xavier(self.tail[-1], gain=1e-5)
         self._init_plans()
 
     def forward(self, x, t):

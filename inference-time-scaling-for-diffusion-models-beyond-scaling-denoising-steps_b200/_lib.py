@@ -124,6 +124,13 @@ def require_cuda():
     lib()
 
 
-def stream_ptr() -> int:
+def stream_ptr(device=None) -> int:
+    """The caller's current stream.  With `device` (a tensor's device) the stream of THAT device; the library
+    launches into the current CUDA context, so a tensor on another device than the current one is refused."""
     import torch
+    if device is not None and device.type == "cuda":
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        if idx != torch.cuda.current_device():
+            raise RuntimeError(f"its_b200: tensor on cuda:{idx} but the current device is cuda:"
+                               f"{torch.cuda.current_device()} (wrap the call in torch.cuda.device(...))")
     return torch.cuda.current_stream().cuda_stream

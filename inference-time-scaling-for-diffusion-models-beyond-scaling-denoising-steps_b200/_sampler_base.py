@@ -33,6 +33,7 @@ class _Trajectory:
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.noise_buf: Optional[torch.Tensor] = None
         self.key = None
+        self.plan = None      # the captured graph bakes pointers into this plan: holding it keeps them alive
 
 
 class SamplerBase(nn.Module):
@@ -95,7 +96,14 @@ class SamplerBase(nn.Module):
         L = _lib.lib()
         if x_T.device.type != "cuda":
             raise RuntimeError("its_b200 samplers run on CUDA only (no CPU fallback)")
+        with torch.cuda.device(x_T.device):   # every launch below goes to this device's current stream
+            return self._sample_on_device(L, x_T, labels, noise=noise, seed=seed, cand_id0=cand_id0, t_start=t_start,
+                                          clip=clip, check_nan=check_nan, t_stop=t_stop)
+
+    def _sample_on_device(self, L, x_T, labels, *, noise, seed, cand_id0, t_start, clip, check_nan, t_stop):
         net = self._unet()
+        if net.head.weight.device != x_T.device:
+            raise RuntimeError(f"x_T lives on {x_T.device} but the UNet on {net.head.weight.device}")
         B, Cc, H, W = x_T.shape
         n_net = 2 * B if self.guided else B
         plan = net.plan(n_net, H, W, n_img_in=B, uniform_t=True, impl=getattr(net, "impl", None))
@@ -109,10 +117,13 @@ class SamplerBase(nn.Module):
         t_stop = int(t_stop)
         if not (0 <= t_stop <= first):
             raise ValueError(f"t_stop={t_stop} outside [0, t_start={first}]")
-        key = (id(plan), noise is not None, clip, tuple(noise.shape) if noise is not None else None)
+        key = (noise is not None, clip, tuple(noise.shape) if noise is not None else None)
         tr = self._traj.get(key)
+        if tr is not None and tr.plan is not plan:
+            tr = None             # the plan was rebuilt (load_state_dict / .to() / new batch): never replay its graph
         if tr is None:
             tr = _Trajectory()
+            tr.plan = plan
             tr.nan_flag = torch.zeros(1, dtype=torch.int32, device=x_T.device)
             tr.seed_args = None
             if noise is not None:
@@ -146,7 +157,9 @@ class SamplerBase(nn.Module):
 
         t_cur = first
         graph_ok = self.use_cuda_graph and first - t_stop >= 2
-        if graph_ok and (tr.graph is None or tr.seed_args != (seed, cand_id0, w)):
+        # with injected noise the Philox key is never read: keep it out of the graph key
+        graph_key = (None, 0, w) if noise is not None else (seed, cand_id0, w)
+        if graph_ok and (tr.graph is None or tr.seed_args != graph_key):
             # (re)capture: seed / candidate base / guidance weight are baked into the graph.
             # One eager step first: it is a real step and it performs the lazy one-time
             # kernel attribute setup outside of stream capture.
@@ -157,7 +170,7 @@ class SamplerBase(nn.Module):
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 step()
-            tr.graph, tr.seed_args = g, (seed, cand_id0, w)
+            tr.graph, tr.seed_args = g, graph_key
         while t_cur >= t_stop:
             if self.print_steps:
                 print(t_cur)

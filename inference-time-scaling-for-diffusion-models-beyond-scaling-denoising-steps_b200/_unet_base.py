@@ -52,13 +52,16 @@ class PlannedUNet(nn.Module):
             raise RuntimeError("its_b200 UNet runs on CUDA only (no CPU fallback)")
         if x.dim() != 4 or x.shape[1] != 3:
             raise ValueError(f"expected x of shape [B,3,H,W], got {tuple(x.shape)}")
+        if self.head.weight.device != x.device:
+            raise RuntimeError(f"x lives on {x.device} but the UNet on {self.head.weight.device}")
         B, _, H, W = x.shape
-        p = self.plan(B, H, W, impl=getattr(self, "impl", None))
-        with torch.no_grad():
-            p.x_in.copy_(x)
-            p.t_idx.copy_(t.reshape(-1).to(torch.int64))
-            if labels is not None:
-                p.labels.copy_(labels.reshape(-1).to(torch.int64))
-        p.run_label_ops()
-        p.run()
-        return p.eps.clone()
+        with torch.cuda.device(x.device):     # launches go to this device's current stream
+            p = self.plan(B, H, W, impl=getattr(self, "impl", None))
+            with torch.no_grad():
+                p.x_in.copy_(x)
+                p.t_idx.copy_(t.reshape(-1).to(torch.int64))
+                if labels is not None:
+                    p.labels.copy_(labels.reshape(-1).to(torch.int64))
+            p.run_label_ops()
+            p.run()
+            return p.eps.clone()

@@ -190,11 +190,9 @@ extern "C" int its_attention_small(void* out, const void* qkv, int32_t n_img, in
   }
   const size_t smem = (size_t)3 * N * (C + 8) * 2 + 8 * its::AS_QB * 64 * 4;
   ITS_REQUIRE(smem <= 227 * 1024, "its_attention_small: N=%d C=%d needs %zu bytes of shared memory", N, C, smem);
-  static size_t configured = 0;
-  if (smem > configured) {
+  static its::PerDeviceBytes configured;
+  if (configured.need(smem))
     ITS_CHECK_CUDA(cudaFuncSetAttribute(its::attention_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
   ITS_LAUNCH(its::attention_small_kernel, dim3(n_img), dim3(256), smem, its::as_stream(stream),
       static_cast<__nv_bfloat16*>(out), static_cast<const __nv_bfloat16*>(qkv), N, C, scale);
   ITS_CHECK_LAUNCH();

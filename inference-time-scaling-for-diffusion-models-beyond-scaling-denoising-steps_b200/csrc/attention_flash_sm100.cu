@@ -356,11 +356,9 @@ static int launch_flash(const FlashParams& p, const CUtensorMap& tmQ, const CUte
                         const CUtensorMap& tmO, int n_img, cudaStream_t stream) {
   using L = FlashSmem<C>;
   static_assert(L::TOTAL <= 227 * 1024, "shared memory budget");
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceBytes configured;
+  if (configured.need(L::TOTAL))
     ITS_CHECK_CUDA(cudaFuncSetAttribute(attention_flash_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
-    configured = true;
-  }
   ITS_LAUNCH(attention_flash_kernel<C>, dim3(p.N / 128, n_img), dim3(FL_THREADS), (size_t)L::TOTAL, stream, p, tmQ, tmK,
              tmV, tmO);
   return ITS_OK;

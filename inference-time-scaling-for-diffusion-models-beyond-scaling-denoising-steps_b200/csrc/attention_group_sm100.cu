@@ -290,11 +290,9 @@ extern "C" int its_attention_group(void* out, const void* qkv, const float* bias
   p.C = C;
   p.n_shift = (N == 16) ? 4 : (N == 32) ? 5 : 6;
   p.scale_log2e = scale * 1.4426950408889634f;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceBytes configured;
+  if (configured.need(AG_SMEM))
     ITS_CHECK_CUDA(cudaFuncSetAttribute(attention_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AG_SMEM));
-    configured = true;
-  }
   const unsigned groups = (unsigned)((rows + 127) / 128);
   ITS_LAUNCH(attention_group_kernel, dim3(groups), dim3(AG_THREADS), (size_t)AG_SMEM, as_stream(stream), p, tmQK, tmV, tmO);
   return ITS_OK;

@@ -318,11 +318,9 @@ extern "C" int its_attention_fused(void* out, const void* qk, const void* vT, co
   p.C = C;
   p.scale_log2e = scale * 1.4426950408889634f;
   p.v_mn = v_mn ? 1 : 0;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceBytes configured;
+  if (configured.need(AT_SMEM))
     ITS_CHECK_CUDA(cudaFuncSetAttribute(attention_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
-    configured = true;
-  }
   ITS_LAUNCH(attention_fused_kernel, dim3(N / 128, n_img), dim3(AT_THREADS), (size_t)AT_SMEM, as_stream(stream), p, tmQ,
              tmK, tmV, tmO);
   return ITS_OK;

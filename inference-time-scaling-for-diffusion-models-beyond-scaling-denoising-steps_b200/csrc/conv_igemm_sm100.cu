@@ -410,11 +410,9 @@ static int launch_variant(const TapGemmParams& p, const CUtensorMap* tmA, const 
                           cudaStream_t stream) {
   using L = SmemLayout<BN, STAGES>;
   auto kern = tapgemm_sm100_kernel<BN, STAGES, MIN_CTAS, CS>;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceBytes configured;
+  if (configured.need(L::TOTAL))
     ITS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
-    configured = true;
-  }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(p.tiles_x * p.tiles_y * p.tiles_b, (p.Cout + BN - 1) / BN, p.nphases * p.splits);
   cfg.blockDim = dim3(NUM_THREADS, 1, 1);

@@ -646,13 +646,12 @@ tapgemm_persist_kernel(const __grid_constant__ TapGemmParams p, const __grid_con
 
 // ---------------------------------------------------------------- host ----
 int device_sm_count() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
-    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
-  }
-  return n;
+  static int n[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  int& c = n[dev & 63];
+  if (c == 0 && (cudaDeviceGetAttribute(&c, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || c <= 0)) c = 148;
+  return c;
 }
 
 static int persist_bn(const its_conv_desc* d, const TapGemmParams& p) {
@@ -700,11 +699,9 @@ static int launch_persist_fmt(const TapGemmParams& p, const CUtensorMap* tmA, co
   using L = PersistSmem<BN, STAGES, MT, KS, TM>;
   static_assert(L::TOTAL <= 227 * 1024, "shared memory budget");
   auto kern = tapgemm_persist_kernel<BN, STAGES, MT, KS, TM, F16>;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceBytes configured;
+  if (configured.need(L::TOTAL))
     ITS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
-    configured = true;
-  }
   const int tiles = p.tiles_x * (p.tiles_y / MT) * p.tiles_b * (p.Cout / BN) * p.nphases * p.splits;
   const int sms = device_sm_count();
   cudaLaunchConfig_t cfg = {};

@@ -377,11 +377,9 @@ __global__ void __launch_bounds__(GN_THREADS, 4) gn_apply_stats_kernel(const GnS
 template <bool CACHE>
 static int launch_gn_cluster(const GnArgs& a, int n_img, size_t dyn_bytes, cudaStream_t stream) {
   auto kern = gn_cluster_kernel<CACHE>;
-  static size_t configured = 0;
-  if (dyn_bytes > configured) {
+  static PerDeviceBytes configured;
+  if (dyn_bytes > 0 && configured.need(dyn_bytes))
     ITS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_bytes));
-    configured = dyn_bytes;
-  }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(a.chunks, n_img, 1);
   cfg.blockDim = dim3(GN_THREADS, 1, 1);

@@ -32,6 +32,22 @@ int set_error(int code, const char* fmt, ...);
 
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
+// cudaFuncSetAttribute acts on the current device only: the "already configured" caches of the launchers are
+// kept per device (one process normally drives one GPU, but a model on a second device must not inherit the
+// first device's flag).
+struct PerDeviceBytes {
+  size_t v[64] = {};
+  // true when the kernel attribute must be (re)set to hold `bytes` of dynamic shared memory on the current device
+  bool need(size_t bytes) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+    dev &= 63;
+    if (bytes <= v[dev]) return false;
+    v[dev] = bytes;
+    return true;
+  }
+};
+
 // Programmatic dependent launch: every kernel of the library starts with pdl_prologue()
 // (release the next launch, then wait for the previous grid's memory to be visible), so
 // consecutive launches on a stream overlap their launch latency / set-up with the tail of

@@ -316,6 +316,13 @@ def main(argv: Optional[List[str]] = None) -> int:
     device = torch.device(cfg.get("device", "cuda"))
     if device.type == "cuda" and device.index is None:
         device = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    if device.type == "cuda":
+        torch.cuda.set_device(device)       # the library launches on the current device's current stream
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1 and not torch.distributed.is_initialized():
+        # one process per GPU: the searches shard their candidates over the ranks (scores all-gathered)
+        torch.distributed.init_process_group("nccl" if device.type == "cuda" else "gloo",
+                                             **({"device_id": device} if device.type == "cuda" else {}))
     model = create_and_load_model(cfg, device)
     sampler = create_sampler(model, cfg, device)
     sampler.print_steps = False

@@ -154,9 +154,10 @@ def philox_normal(shape: Sequence[int], seed: int, cand_id0: int, tag: int, devi
     n_img = shape[0]
     n_per = out.numel() // n_img
     b = None if base is None else base.to(device=device, dtype=torch.float32).contiguous()
-    _lib.check(_lib.lib().its_philox_normal(out.data_ptr(), None if b is None else b.data_ptr(), 1, float(scale),
-                                            n_img, n_per, seed, cand_id0, tag, _lib.stream_ptr()),
-               "its_philox_normal")
+    with torch.cuda.device(out.device):
+        _lib.check(_lib.lib().its_philox_normal(out.data_ptr(), None if b is None else b.data_ptr(), 1, float(scale),
+                                                n_img, n_per, seed, cand_id0, tag, _lib.stream_ptr(out.device)),
+                   "its_philox_normal")
     return out
 
 
@@ -166,8 +167,9 @@ def argmax_first(scores: torch.Tensor) -> Tuple[int, float]:
     s = scores.detach().to(torch.float32).contiguous()
     idx = torch.empty(1, dtype=torch.int32, device=s.device)
     val = torch.empty(1, dtype=torch.float32, device=s.device)
-    _lib.check(_lib.lib().its_argmax_first(idx.data_ptr(), val.data_ptr(), s.data_ptr(), s.numel(),
-                                           _lib.stream_ptr()), "its_argmax_first")
+    with torch.cuda.device(s.device):
+        _lib.check(_lib.lib().its_argmax_first(idx.data_ptr(), val.data_ptr(), s.data_ptr(), s.numel(),
+                                               _lib.stream_ptr(s.device)), "its_argmax_first")
     return int(idx.item()), float(val.item())
 
 
@@ -440,6 +442,8 @@ def _run_prefix(denoise: SamplerDenoiser, x_T: torch.Tensor, stop_step: int, lab
     smp = denoise.sampler
     seed = denoise.seed if denoise.seed is not None else 0
     kw = dict(seed=seed, cand_id0=0, t_stop=stop_step, clip=False)
+    if denoise.step_noise is not None:          # parity runs: the pivot's prefix uses the injected Gaussians too
+        kw["noise"] = denoise.step_noise
     if getattr(smp, "guided", False):
         lab = (labels if labels is not None else denoise.labels).reshape(-1).to(x_T.device, torch.int64)
         return smp(x_T, lab, **kw)

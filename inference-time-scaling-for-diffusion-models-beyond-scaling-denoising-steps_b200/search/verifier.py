@@ -32,8 +32,9 @@ def _stats(images: torch.Tensor, want_feats: bool):
     stats = torch.empty((n, 4), dtype=torch.float32, device=x.device)
     feats = torch.empty((n, c * 64), dtype=torch.float32, device=x.device) if want_feats else None
     L = _lib.lib()
-    _lib.check(L.its_image_stats(stats.data_ptr(), feats.data_ptr() if want_feats else None, x.data_ptr(),
-                                 n, c, h, w, _lib.stream_ptr()), "its_image_stats")
+    with torch.cuda.device(x.device):
+        _lib.check(L.its_image_stats(stats.data_ptr(), feats.data_ptr() if want_feats else None, x.data_ptr(),
+                                     n, c, h, w, _lib.stream_ptr(x.device)), "its_image_stats")
     return stats, feats
 
 
@@ -45,10 +46,11 @@ def candidate_scores(images: torch.Tensor, per_cand: int, kind: int) -> torch.Te
     stats, feats = _stats(images, kind == KIND_SELFSUP)
     scores = torch.empty((n // per_cand,), dtype=torch.float32, device=images.device)
     L = _lib.lib()
-    _lib.check(L.its_candidate_scores(scores.data_ptr(), stats.data_ptr(),
-                                      feats.data_ptr() if feats is not None else None, n // per_cand,
-                                      per_cand, images.shape[1] * 64, kind, _lib.stream_ptr()),
-               "its_candidate_scores")
+    with torch.cuda.device(images.device):
+        _lib.check(L.its_candidate_scores(scores.data_ptr(), stats.data_ptr(),
+                                          feats.data_ptr() if feats is not None else None, n // per_cand,
+                                          per_cand, images.shape[1] * 64, kind, _lib.stream_ptr(images.device)),
+                   "its_candidate_scores")
     return scores
 
 

@@ -215,14 +215,16 @@ def p_mean_variance(sd, sched, x_t: Tensor, t: Tensor, labels: Optional[Tensor] 
 
 def sample(sd, sched, x_T: Tensor, noise_fn: Callable[[int], Tensor], labels: Optional[Tensor] = None,
            w: float = 0.0, quant: Optional[str] = None, t_start: Optional[int] = None,
-           clip: bool = True) -> Tensor:
+           clip: bool = True, t_stop: int = 0) -> Tensor:
     """Ancestral loop with injected noise: Diffusion.py:84-102 /
     DiffusionCondition.py:89-105.  noise_fn(time_step) supplies z for steps
-    T-1 .. 1 (the reference draws exactly T-1 tensors, none at step 0)."""
+    T-1 .. 1 (the reference draws exactly T-1 tensors, none at step 0).
+    t_start / t_stop cut the same loop into segments (steps t_start .. t_stop inclusive): the mid-trajectory
+    restart of search over paths (BASELINE config 4) is two such segments with a perturbation in between."""
     T = sched["betas"].shape[0]
     x_t = x_T
     first = T - 1 if t_start is None else t_start
-    for time_step in range(first, -1, -1):
+    for time_step in range(first, t_stop - 1, -1):
         t = torch.full((x_T.shape[0],), time_step, dtype=torch.long)
         mean, var, _ = p_mean_variance(sd, sched, x_t, t, labels, w, quant)
         if time_step > 0:
@@ -314,6 +316,27 @@ def path_search(initial: Tensor, variations: Sequence[Tensor], noise_scale: floa
         if s > best:
             best, best_noise = s, z.clone()
     return best_noise, best, history
+
+
+def path_search_restart(sd, sched, initial: Tensor, variations: Sequence[Tensor], noise_scale: float,
+                        injection_step: int, noise_fn, verifier_fn, labels: Optional[Tensor] = None,
+                        w: float = 0.0):
+    """Search over paths with a real mid-trajectory restart (the paper's semantics, which the reference's
+    placeholder at search/search_algorithm.py:307-312 announces but does not implement; BASELINE config 4):
+    the pivot trajectory runs steps T-1 .. injection_step once; every path perturbs that intermediate state
+    by noise_scale * variation and finishes steps injection_step-1 .. 0; strict '>' keeps the first best.
+    Returns (best perturbed state, best score, history)."""
+    base = sample(sd, sched, initial, noise_fn, labels, w, t_stop=injection_step, clip=False)
+    best_state, best = base.clone(), float("-inf")
+    history = {"scores": [], "injection_points": []}
+    for v in variations:
+        x = base + v * noise_scale
+        s = verifier_fn(sample(sd, sched, x, noise_fn, labels, w, t_start=injection_step - 1))
+        history["scores"].append(s)
+        history["injection_points"].append(injection_step)
+        if s > best:
+            best, best_state = s, x.clone()
+    return best_state, best, history
 
 
 # ------------------------------------------------------------ synthetic init --

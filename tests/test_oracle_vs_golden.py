@@ -158,3 +158,25 @@ def test_gradient_based_search_matches_reference_on_differentiable_callables():
         assert rs == bs and torch.equal(rn, bn)
     with pytest.raises(TypeError):
         gs.search(z0, S.SamplerDenoiser(None), verify)
+
+
+def test_shell_constructor_reproduces_the_reference_init():
+    """BASELINE north_star: "the same random-init weights".  torch.manual_seed(0) + the shell's constructor draws
+    the parameters of the reference's constructor bit for bit (same modules created and re-initialised in the same
+    order, including Model.py:199-204's re-initialisation of the attention projections inside ResBlock.initialize):
+    checked against checksums of the reference's state dict stored by tests/golden/make_golden_long2.py."""
+    cfg = cases.LONG_CASES["u_A_refinit"]
+    g = golden("smp_u_A_refinit")
+    from its_b200.Diffusion import UNet
+    torch.manual_seed(cfg["init_seed"])
+    m = UNet(T=cfg["T"], ch=cfg["ch"], ch_mult=cfg["ch_mult"], attn=cfg["attn"],
+             num_res_blocks=cfg["num_res_blocks"], dropout=cfg["dropout"])
+    sd = m.state_dict()
+    assert len(sd) == len(g["sd_sums"]) == 333
+    sums = np.array([float(v.double().sum()) for v in sd.values()])
+    sq = np.array([float(v.double().pow(2).sum()) for v in sd.values()])
+    # the checksums are fp64 sums of fp32 values: equal up to the summation order of the two runs
+    assert np.abs(sums - g["sd_sums"]).max() < 1e-9
+    assert (np.abs(sq - g["sd_sq"]) / np.maximum(g["sd_sq"], 1e-30)).max() < 1e-12
+    # the quirk: attention output projections inside ResBlocks end with gain 1, block2's conv with gain 1e-5
+    assert sd["downblocks.3.attn.proj.weight"].abs().max() > 1e-2 > sd["downblocks.3.block2.3.weight"].abs().max()
