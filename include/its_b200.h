@@ -247,6 +247,22 @@ typedef struct {
   int32_t out_fp16;      /* bit 0: 16-bit NHWC output in IEEE fp16 instead of bf16 (the opt-in
                             fp16 residual stream: 3 more mantissa bits, 65504 range);
                             bit 1: `res` holds IEEE fp16                               */
+  /* GroupNorm (+ Swish) of the tensor this launch computes, applied in the SAME launch's epilogue
+   * (Model.py:170-173,186-190,132: the GroupNorm -> Swish that opens the next convolution or the attention
+   * block reads exactly the tensor this convolution produces).  Persistent schedule only, one phase,
+   * out_scale 1; see its_conv_gn_sync_words() for the shapes it covers.  The statistics are the ones
+   * `stats` receives (they must be requested); a tile whose image spans several tiles waits for exactly
+   * those peer tiles (consecutive work items, co-resident CTAs) through the `gn_sync` counters.        */
+  void* gn_out;          /* out, optional: IEEE fp16 [B][Hm][Wm][gn_c_pitch] = Swish?(GroupNorm(D))       */
+  int32_t gn_c_pitch;
+  const float* gn_gamma; /* [Cout] affine weight / bias of that GroupNorm                                 */
+  const float* gn_beta;
+  int32_t gn_groups;     /* groups over the Cout channels (32 in both nets)                               */
+  float gn_eps;
+  int32_t gn_silu;       /* 1: Swish after the normalisation                                              */
+  int32_t gn_only;       /* 1: `out` (the raw tensor) is not stored, only gn_out (ResBlock conv1 -> block2)*/
+  int32_t* gn_sync;      /* its_conv_gn_sync_words() counters, zero-initialised ONCE (they only count up:
+                            every launch adds `peers` to each), or NULL when that count is 0              */
 } its_conv_desc;
 
 int its_conv_igemm(const its_conv_desc* desc_host, int32_t impl, void* stream);
@@ -255,6 +271,12 @@ int its_conv_igemm(const its_conv_desc* desc_host, int32_t impl, void* stream);
  * desc->stats for this descriptor's tiling, or 0 when the layer cannot run on
  * the persistent schedule (no statistics are produced then).               */
 int its_conv_stats_parts(const its_conv_desc* desc_host);
+
+/* Whether the epilogue of this descriptor can apply the GroupNorm of its own output (gn_out & co.), and how many
+ * peer-tile counters that takes: -1 = not fusable (run its_group_norm_apply on the stored tensor instead),
+ * 0 = fusable, every tile holds whole images (4x4 / 8x8 maps), n > 0 = fusable, desc->gn_sync must point to n
+ * ints zero-initialised once.  desc->gn_groups, bn, splits and schedule must already be set.                  */
+int its_conv_gn_sync_words(const its_conv_desc* desc_host);
 
 /* ------------------------------------------------------------------------
  * Attention pieces (Model.py:153-158): row softmax of fp32 scores -> bf16
@@ -317,6 +339,41 @@ int its_candidate_scores(float* scores, const float* stats, const float* feats,
                          int32_t kind, void* stream);
 int its_argmax_first(int32_t* idx_out, float* val_out, const float* scores,
                      int32_t n, void* stream);
+
+/* ------------------------------------------------------------------------
+ * fp32-grade path (precision = "fp32").  The reference computes everything in
+ * fp32 (Diffusion/Diffusion.py:74-99 over Model.py / ModelCondition.py) and
+ * north_star states 1e-4 on the samples for that mode: plain CUDA-core kernels
+ * over NHWC fp32 tensors, one per reference operation, fp32 FMAs in a fixed
+ * order, GroupNorm statistics in double.  A parity instrument and an on-device
+ * cross-check of the tcgen05 path, not the throughput path.
+ *   its_f32_nchw_to_nhwc: out[b][y][x][c] = in[b % n_img_in][c][y][x]
+ *   its_f32_conv2d: convolution over the channel concatenation (in0 | in1) of
+ *     NHWC tensors [B][Hin][Win][C0], [..][C1]; Wt = [k*k][C0+C1][CoutP] fp32
+ *     (tap, input channel, output channel; CoutP = Cout rounded up to 4);
+ *     + bias[n] + vec[b*vec_stride+n] + vec2[..] + res[(b,y,x),n].
+ *     mode 0: nn.Conv2d(k, stride, k/2)           Model.py:99,173,190,193,262,269
+ *     mode 1: nearest x2 up-sampling, then mode 0 (stride 1)     Model.py:122-125
+ *     mode 2: nn.ConvTranspose2d(k, 2, k/2, 1); Wt taps from the [Cin][Cout][k][k]
+ *             weight, unflipped                                ModelCondition.py:80
+ *     out NHWC fp32, or NCHW when out_nchw (the 3-channel tail, Model.py:262).
+ *   its_f32_group_norm: nn.GroupNorm(groups, C0+C1) (+ Swish) of (in0 | in1),
+ *     out NHWC [n_img][HW][C0+C1].            Model.py:132,170-173,186-190,257-259
+ *   its_f32_attention: out[b,i,:] = softmax_j(scale q_i.k_j) v_j over the fused
+ *     projection tensor qkv [n_img][N][3C].                      Model.py:147-161
+ * ---------------------------------------------------------------------- */
+int its_f32_nchw_to_nhwc(float* out, const float* in, int32_t n_img, int32_t n_img_in,
+                         int32_t C, int32_t H, int32_t W, void* stream);
+int its_f32_conv2d(float* out, const float* in0, int32_t C0, const float* in1, int32_t C1,
+                   const float* Wt, const float* bias, const float* vec, int32_t vec_stride,
+                   const float* vec2, int32_t vec2_stride, const float* res, int32_t B,
+                   int32_t Hin, int32_t Win, int32_t Cout, int32_t k, int32_t stride,
+                   int32_t mode, int32_t out_nchw, void* stream);
+int its_f32_group_norm(float* out, const float* in0, int32_t C0, const float* in1, int32_t C1,
+                       const float* gamma, const float* beta, int32_t n_img, int32_t HW,
+                       int32_t groups, float eps, int32_t silu, void* stream);
+int its_f32_attention(float* out, const float* qkv, int32_t n_img, int32_t N, int32_t C,
+                      float scale, void* stream);
 
 #ifdef __cplusplus
 }

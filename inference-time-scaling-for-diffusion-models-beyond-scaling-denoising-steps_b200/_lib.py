@@ -19,7 +19,8 @@ SYMBOLS = [
     "its_group_norm", "its_conv_head", "its_conv_tail", "its_conv_igemm", "its_softmax_rows",
     "its_attention_small", "its_image_stats", "its_candidate_scores", "its_argmax_first",
     "its_group_norm_apply", "its_conv_stats_parts", "its_set_pdl", "its_attention_fused", "its_head_patches",
-    "its_attention_flash", "its_attention_group",
+    "its_attention_flash", "its_attention_group", "its_conv_gn_sync_words",
+    "its_f32_nchw_to_nhwc", "its_f32_conv2d", "its_f32_group_norm", "its_f32_attention",
 ]
 
 
@@ -52,6 +53,9 @@ class ConvDesc(C.Structure):
         ("cluster", C.c_int32), ("dbg", C.c_void_p),
         ("stats", C.c_void_p), ("stats_parts", C.c_int32), ("schedule", C.c_int32),
         ("out_fp16", C.c_int32),
+        ("gn_out", C.c_void_p), ("gn_c_pitch", C.c_int32), ("gn_gamma", C.c_void_p), ("gn_beta", C.c_void_p),
+        ("gn_groups", C.c_int32), ("gn_eps", C.c_float), ("gn_silu", C.c_int32), ("gn_only", C.c_int32),
+        ("gn_sync", C.c_void_p),
     ]
 
 
@@ -86,6 +90,7 @@ def lib() -> C.CDLL:
     L.its_group_norm.argtypes = [vp, vp, i32, vp, i32, vp, vp, i32, i32, i32, f32, i32, vp, i32, i32, vp]
     L.its_group_norm_apply.argtypes = [vp, vp, i32, vp, i32, vp, i32, vp, i32, vp, vp, i32, i32, i32, f32, i32, i32, vp]
     L.its_conv_stats_parts.argtypes = [C.POINTER(ConvDesc)]
+    L.its_conv_gn_sync_words.argtypes = [C.POINTER(ConvDesc)]
     L.its_conv_head.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]
     L.its_head_patches.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp]
     L.its_conv_tail.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]
@@ -95,6 +100,10 @@ def lib() -> C.CDLL:
     L.its_attention_fused.argtypes = [vp, vp, vp, vp, i32, i32, i32, f32, vp]
     L.its_attention_flash.argtypes = [vp, vp, vp, vp, i32, i32, i32, f32, vp]
     L.its_attention_group.argtypes = [vp, vp, vp, i32, i32, i32, f32, vp]
+    L.its_f32_nchw_to_nhwc.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp]
+    L.its_f32_conv2d.argtypes = [vp, vp, i32, vp, i32, vp, vp, vp, i32, vp, i32, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp]
+    L.its_f32_group_norm.argtypes = [vp, vp, i32, vp, i32, vp, vp, i32, i32, i32, f32, i32, vp]
+    L.its_f32_attention.argtypes = [vp, vp, i32, i32, i32, f32, vp]
     L.its_image_stats.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp]
     L.its_candidate_scores.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp]
     L.its_argmax_first.argtypes = [vp, vp, vp, i32, vp]

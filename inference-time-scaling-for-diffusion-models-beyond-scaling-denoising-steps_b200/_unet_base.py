@@ -12,6 +12,7 @@ import torch
 from torch import nn
 
 from .engine import UNetPlan
+from .engine_f32 import UNetPlanF32
 
 
 class ParamOnly(nn.Module):
@@ -39,11 +40,19 @@ class PlannedUNet(nn.Module):
 
     def plan(self, n_img: int, H: int, W: int, *, n_img_in: Optional[int] = None, uniform_t: bool = False,
              impl: Optional[int] = None) -> UNetPlan:
+        # `precision`: "16bit" (default; fp16 / bf16 operands on the tensor cores, fp32 accumulation: the
+        # throughput path, samples within 2e-2 of the fp32 reference) or "fp32" (CUDA-core fp32 kernels, the parity
+        # path: samples within 1e-4).  Set it on the model (`net.precision = "fp32"`) or through ITS_PRECISION.
+        import os
+        precision = str(getattr(self, "precision", None) or os.environ.get("ITS_PRECISION", "16bit")).lower()
+        if precision not in ("16bit", "fp32"):
+            raise ValueError(f"precision {precision!r}: '16bit' or 'fp32'")
         key = (n_img, H, W, n_img_in or n_img, uniform_t, impl, self.head.weight.data_ptr(),
-               bool(getattr(self, "residual_fp16", False)))
+               bool(getattr(self, "residual_fp16", False)), precision)
         p = self._plans.get(key)
         if p is None:
-            p = UNetPlan(self, n_img, H, W, n_img_in=n_img_in, uniform_t=uniform_t, impl=impl)
+            cls = UNetPlanF32 if precision == "fp32" else UNetPlan
+            p = cls(self, n_img, H, W, n_img_in=n_img_in, uniform_t=uniform_t, impl=impl)
             self._plans[key] = p
         return p
 

@@ -315,6 +315,9 @@ int tapgemm_build_params(const its_conv_desc* d, TapGemmParams* p, bool need_k64
   p->res = d->res ? static_cast<const __nv_bfloat16*>(d->res) + d->res_c_off : nullptr;
   p->res_c_pitch = d->res_c_pitch;
   p->alpha = d->alpha;
+  p->gn_out = d->gn_out; p->gn_c_pitch = d->gn_c_pitch; p->gn_gamma = d->gn_gamma; p->gn_beta = d->gn_beta;
+  p->gn_groups = d->gn_groups; p->gn_eps = d->gn_eps; p->gn_silu = d->gn_silu; p->gn_only = d->gn_only;
+  p->gn_sync = d->gn_sync;
   // M tiling (used by the tcgen05 kernel): box of 128 GEMM rows
   int bw = d->Wm < 128 ? d->Wm : 128;
   int bh = 128 / bw; if (bh > d->Hm) bh = d->Hm;
@@ -399,6 +402,8 @@ extern "C" int its_conv_igemm(const its_conv_desc* desc_host, int32_t impl, void
   int rc = tapgemm_build_params(desc_host, &p, impl == 0);
   if (rc != ITS_OK) return rc;
   ITS_REQUIRE(desc_host->schedule >= 0 && desc_host->schedule <= 2, "its_conv_igemm: schedule=%d", desc_host->schedule);
+  ITS_REQUIRE(p.gn_out == nullptr || (impl == 0 && desc_host->schedule != 1),
+              "its_conv_igemm: the fused GroupNorm epilogue needs the persistent tcgen05 schedule");
   if (impl == 1) {
     ITS_REQUIRE(p.stats == nullptr, "its_conv_igemm: GroupNorm statistics need the persistent tcgen05 schedule");
     return tapgemm_launch_ref(p, as_stream(stream));
@@ -408,7 +413,16 @@ extern "C" int its_conv_igemm(const its_conv_desc* desc_host, int32_t impl, void
   ITS_REQUIRE(persist || desc_host->schedule != 2, "its_conv_igemm: schedule=2 but the layer is not eligible for the persistent kernel");
   if (persist) return tapgemm_launch_persist(desc_host, p, as_stream(stream));
   ITS_REQUIRE(p.stats == nullptr, "its_conv_igemm: GroupNorm statistics need the persistent tcgen05 schedule");
+  ITS_REQUIRE(p.gn_out == nullptr, "its_conv_igemm: the fused GroupNorm epilogue needs the persistent tcgen05 schedule");
   return tapgemm_launch_sm100(desc_host, p, as_stream(stream));
+}
+
+extern "C" int its_conv_gn_sync_words(const its_conv_desc* desc_host) {
+  using namespace its;
+  TapGemmParams p;
+  if (tapgemm_build_params(desc_host, &p, true) != ITS_OK) return -1;
+  if (desc_host->schedule == 1 || !tapgemm_persist_eligible(desc_host, p)) return -1;
+  return tapgemm_gn_sync_words(desc_host, p);
 }
 
 extern "C" int its_conv_stats_parts(const its_conv_desc* desc_host) {

@@ -156,17 +156,110 @@ __device__ __forceinline__ void column_pair_sums(uint32_t sbuf_addr, int r8, int
   }
 }
 
+// ---- fused GroupNorm(+Swish) epilogue ---------------------------------------------------------------
+// The GroupNorm that opens the consumer of this convolution (Model.py:170-173,186-190,132) is applied by the
+// epilogue that produces the tensor: pass 1 is the ordinary epilogue (raw 16-bit panel staged, its column sums
+// written to the partial-sum array, the raw TMA store skipped when nobody reads the raw tensor); then the tiles
+// an image spans meet (gn_peer_rendezvous), every tile reduces the image's partial sums to mean / rstd per
+// group, and pass 2 re-reads the fp32 accumulators from TMEM, applies (x - mean) * rstd * gamma + beta (+ Swish)
+// and stores the IEEE fp16 result through a second tensor map.  The accumulator buffer is released after pass 2.
+//
+// Peer tiles = the M tiles of one image with the same N tile: consecutive work items, hence on different,
+// co-resident CTAs (grid <= SM count, one CTA per SM).  No deadlock: the arrival of work item w needs only the
+// epilogue of item w - grid on the same CTA to finish, which waits for arrivals of items < w - grid + peers <= w,
+// so "arrives" is well founded in the item index.  The counter only ever counts up: all `peers` arrivals of one
+// launch precede every arrival of the next launch (kernel boundary), so the value a tile's own atomicAdd returns
+// tells it which multiple of `peers` to wait for (peers is a power of two, so the grouping survives the 32-bit
+// wrap-around) — no reset, no second counter.  Called by one thread between two CTA barriers: its fences are
+// cumulative over the partial sums the other threads stored before the first barrier (the pattern of
+// cooperative groups' grid sync).
+__device__ __forceinline__ void gn_peer_rendezvous(unsigned* counter, unsigned peers) {
+  __threadfence();
+  const unsigned old = atomicAdd(counter, 1u);
+  const unsigned target = (old / peers + 1u) * peers;
+  if (old + 1u != target) {
+    unsigned cur = old;
+    for (uint32_t spin = 0; spin < (1u << 24); ++spin) {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(cur) : "l"(counter) : "memory");
+      if ((int)(cur - target) >= 0) break;
+      __nanosleep(20);
+    }
+    if ((int)(cur - target) < 0) __trap();      // a lost peer would otherwise hang the device
+  }
+  __threadfence();
+}
+
+// mean and 1/sqrt(var + eps) of the (image, group) pairs of a tile from the partial sums [img][part][Cout/4] of
+// float2 in global memory: T = 256 / pairs (at most 32) consecutive lanes share a pair, each sums every T-th
+// entry, xor-shuffle tree, all in double (fixed order; the arithmetic of gn_apply_stats_kernel, groupnorm.cu).
+// Every epilogue thread calls it (full-warp shuffles); lane 0 of a pair writes table[pair].
+__device__ __forceinline__ void gn_tile_stats(float2* table, const float2* stats, int et, int pairs, int ngt, int g0,
+                                              int img0, int n_img, int parts, int nchunk, int cg4, double n, float eps) {
+  int T = P_EPI_THREADS / pairs;
+  if (T > 32) T = 32;
+  const int pr = et / T, l = et - pr * T;
+  const int il = pr / ngt, gl = pr - il * ngt;
+  const long long bi = img0 + il;
+  const bool active = pr < pairs && bi < n_img;
+  double s = 0.0, q = 0.0;
+  if (active) {
+    const float2* base = stats + bi * parts * nchunk + (g0 + gl) * cg4;
+    const int E = parts * cg4;
+    for (int e = l; e < E; e += T) {
+      const int part = e / cg4, kk = e - part * cg4;
+      const float2 v = __ldcg(base + (long long)part * nchunk + kk);
+      s += (double)v.x;
+      q += (double)v.y;
+    }
+  }
+  for (int o = T >> 1; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    q += __shfl_xor_sync(0xffffffffu, q, o);
+  }
+  if (l == 0 && pr < pairs) {
+    float2 mr = make_float2(0.f, 1.f);
+    if (active) {
+      const double mean = s / n;
+      double var = q / n - mean * mean;    // biased, like nn.GroupNorm
+      if (var < 0.0) var = 0.0;
+      mr = make_float2((float)mean, (float)(1.0 / sqrt(var + (double)eps)));
+    }
+    table[pr] = mr;
+  }
+}
+
+// y = acc * A + B, optional Swish (the formulation of gn_apply_stats_kernel: y * rcp(1 + 2^(-y log2 e)))
+__device__ __forceinline__ float gn_act(float acc, float A, float B, bool silu) {
+  const float y = fmaf(acc, A, B);
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * y));
+  return silu ? __fdividef(y, 1.0f + e) : y;
+}
+
+// transposed-accumulator variant: one channel (scalar A, B), 64 pixels
+__device__ __forceinline__ void tm_stage_column_gn(const uint32_t* v, float A, float B, bool silu, uint32_t sbuf_addr,
+                                                   int half, uint32_t chunk, uint32_t col_byte) {
+#pragma unroll
+  for (int i = 0; i < 64; ++i) {
+    const uint32_t prow = (uint32_t)(half * 64 + i);
+    const unsigned short hb = __half_as_ushort(__float2half_rn(gn_act(__uint_as_float(v[i]), A, B, silu)));
+    const uint32_t dst = sbuf_addr + prow * 128u + (((chunk ^ (prow & 7u)) << 4) | col_byte);
+    asm volatile("st.shared.b16 [%0], %1;" ::"r"(dst), "h"(hb) : "memory");
+  }
+}
+
 // TM ("transposed accumulator", Cout tile of 128 with two row boxes): the MMA takes the WEIGHT tile as
 // its A operand (M = 128 channels) and the 256-pixel activation tile as its B operand (N = 256), so a
 // k-block is 4 instructions of N = 256 instead of 8 of N = 128 — measured, an N = 128 tcgen05.mma costs
 // ~98 clocks against its 64-clock floor while N = 256 runs at its 128-clock floor.  The accumulator is
 // then [channel lane][pixel column]; the epilogue transposes it through the swizzled staging panels
 // with 16-bit shared-memory stores, and the GroupNorm statistics become per-thread sums.
-template <int BN, int STAGES, int MT, int KS, bool TM, bool F16>
+template <int BN, int STAGES, int MT, int KS, bool TM, bool F16, bool GN>
 __global__ void __launch_bounds__(P_THREADS, 1)
 tapgemm_persist_kernel(const __grid_constant__ TapGemmParams p, const __grid_constant__ CUtensorMap tmA0,
                        const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
-                       const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut) {
+                       const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut,
+                       const __grid_constant__ CUtensorMap tmGn) {
   using L = PersistSmem<BN, STAGES, MT, KS, TM>;
   // SWIZZLE_128B atoms need 1024-byte alignment; with no static shared memory the dynamic
   // window starts 1024-aligned (checked: a misaligned window traps instead of corrupting)
@@ -218,6 +311,7 @@ tapgemm_persist_kernel(const __grid_constant__ TapGemmParams p, const __grid_con
     tma_prefetch_desc(&tmA0);
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmOut);
+    if constexpr (GN) tma_prefetch_desc(&tmGn);
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
@@ -358,6 +452,10 @@ tapgemm_persist_kernel(const __grid_constant__ TapGemmParams p, const __grid_con
     const int cp = et & 31, r8 = et >> 5;       // statistics role: column pair, 16-row sub-block
     const int st_ch = et & 15, st_ib = et >> 4; // final reduce role: 4-channel chunk, image in sub-tile
     float2* prev_dst = nullptr;                 // deferred final reduce of the previous panel
+    constexpr bool fuse_gn = GN;                // GroupNorm(+Swish) of this tile in a second epilogue pass
+    const bool gn_silu = p.gn_silu != 0;
+    const int gn_cg = fuse_gn ? p.Cout / p.gn_groups : 4;   // channels per group (multiple of 4)
+    const float2* stats2 = reinterpret_cast<const float2*>(p.stats);
     uint32_t j = 0, pc = 0;
     for (int w = blockIdx.x; w < total_items; w += gridDim.x, ++j) {
       const WorkItem wi = decode_item(w, total_tiles, S);
@@ -435,7 +533,7 @@ tapgemm_persist_kernel(const __grid_constant__ TapGemmParams p, const __grid_con
           tmem_ld32_nowait(taddr + 32, v + 32);
           mbar_wait(&pempty_bar[sb], ((P >> 1) & 1u) ^ 1u);
           tmem_wait_ld();
-          if (m == 1) {
+          if (m == 1 && !fuse_gn) {
             tcgen05_fence_before();
             mbar_arrive(&tempty_bar[buf]);
           }
@@ -459,6 +557,47 @@ tapgemm_persist_kernel(const __grid_constant__ TapGemmParams p, const __grid_con
           }
         }
         pc += 4;
+        if constexpr (GN) {
+          // every partial sum of this tile is on its way to global memory; meet the other tiles of the image
+          if (p.gn_peers > 1) {
+            named_bar_sync(1, P_EPI_THREADS);
+            if (et == 0)
+              gn_peer_rendezvous(reinterpret_cast<unsigned*>(p.gn_sync) + c.tb * tiles_n + c.n0 / BN, (unsigned)p.gn_peers);
+          } else {
+            __threadfence();
+          }
+          named_bar_sync(1, P_EPI_THREADS);
+          const int ngt = BN / gn_cg, g0 = c.n0 / gn_cg;
+          gn_tile_stats(red, stats2, et, ngt, ngt, g0, bimg, p.B, p.stats_parts, p.Cout >> 2, gn_cg >> 2,
+                        (double)gn_cg * (double)(p.Hm * p.Wm), p.gn_eps);
+          named_bar_sync(1, P_EPI_THREADS);
+          const float2 mr = red[cglob / gn_cg - g0];
+          const float sc = mr.y * __ldg(p.gn_gamma + cglob);
+          const float gA = p.alpha * sc;
+          const float gB = fmaf(bvs, sc, __ldg(p.gn_beta + cglob) - mr.x * sc);
+#pragma unroll 1
+          for (int m = 0; m < 2; ++m) {
+            const uint32_t P = pc + 2 * m + pn;
+            const uint32_t sb = P & 1u;
+            uint8_t* sbuf = staging + sb * PANEL_BYTES;
+            uint32_t v[64];
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * (MT * BN) +
+                                   (uint32_t)(m * 128 + half * 64);
+            tmem_ld32_nowait(taddr, v);
+            tmem_ld32_nowait(taddr + 32, v + 32);
+            mbar_wait(&pempty_bar[sb], ((P >> 1) & 1u) ^ 1u);
+            tmem_wait_ld();
+            if (m == 1) {                      // accumulators fully read (twice): release the buffer
+              tcgen05_fence_before();
+              mbar_arrive(&tempty_bar[buf]);
+            }
+            tm_stage_column_gn(v, gA, gB, gn_silu, smem_u32(sbuf), half, cc >> 3, (cc & 7u) * 2u);
+            fence_proxy_async_smem();
+            mbar_arrive(&pfull_bar[sb]);
+          }
+          pc += 4;
+          named_bar_sync(1, P_EPI_THREADS);    // red[] holds the statistics table until every thread is done
+        }
         if (dbg != nullptr && et == 0 && j < 8) dbg[24 + j] = clock64();
         continue;
       }
@@ -510,7 +649,7 @@ tapgemm_persist_kernel(const __grid_constant__ TapGemmParams p, const __grid_con
         tmem_ld32_nowait(taddr, v);
         mbar_wait(&pempty_bar[sb], spar ^ 1u);   // the store that last read sbuf has drained it
         tmem_wait_ld();
-        if (pi == MT * NPANEL - 1) {     // accumulators fully read: hand the buffer back to the MMA warp
+        if (pi == MT * NPANEL - 1 && !fuse_gn) {   // accumulators fully read: hand the buffer back to the MMA warp
           tcgen05_fence_before();
           mbar_arrive(&tempty_bar[buf]);
         }
@@ -588,6 +727,106 @@ tapgemm_persist_kernel(const __grid_constant__ TapGemmParams p, const __grid_con
           }
         }
       }
+      if constexpr (GN) {
+        // (1) this tile's partial sums complete in global memory (the last panel's final reduce is still pending)
+        named_bar_sync(1, P_EPI_THREADS);
+        if (prev_dst != nullptr) {
+          const float2* rd = red + ((pc + 1) & 1u) * 128;
+          float S1 = 0.f, Q1 = 0.f;
+          for (int k = 0; k < nsb_img; ++k) {
+            const float2 t2 = rd[(st_ib * nsb_img + k) * 16 + st_ch];
+            S1 += t2.x;
+            Q1 += t2.y;
+          }
+          *prev_dst = make_float2(S1, Q1);
+          prev_dst = nullptr;
+        }
+        // (2) meet the other tiles of the image (maps larger than one tile)
+        if (p.gn_peers > 1) {
+          named_bar_sync(1, P_EPI_THREADS);
+          if (et == 0)
+            gn_peer_rendezvous(reinterpret_cast<unsigned*>(p.gn_sync) + c.tb * tiles_n + c.n0 / BN, (unsigned)p.gn_peers);
+        } else {
+          __threadfence();
+        }
+        named_bar_sync(1, P_EPI_THREADS);
+        // (3) mean / rstd of every (image of this tile, group of this N tile)
+        const int NG = BN / gn_cg, g0 = c.n0 / gn_cg;      // groups inside this N tile, the first of them
+        gn_tile_stats(red, stats2, et, p.bb * NG, NG, g0, c.tb * p.bb, p.B, p.stats_parts, p.Cout >> 2, gn_cg >> 2,
+                      (double)gn_cg * (double)(p.Hm * p.Wm), p.gn_eps);
+        named_bar_sync(1, P_EPI_THREADS);
+        // (4) second pass over the accumulators: normalise, affine, Swish, fp16, staged panel, TMA store.
+        // Scale and shift are formed per 4-channel chunk right where they are used (register pressure).
+#pragma unroll 1
+        for (int pi = 0; pi < MT * NPANEL; ++pi, ++pc) {
+          const int m = pi / NPANEL, pn = pi - m * NPANEL;
+          const int nc = c.n0 + pn * PANEL_COLS + half * 32;
+          const uint32_t sb = pc & 1u, spar = (pc >> 1) & 1u;
+          uint8_t* sbuf = staging + sb * PANEL_BYTES;
+          uint32_t v[32];
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * (MT * BN) +
+                                 (uint32_t)(m * BN + pn * PANEL_COLS + half * 32);
+          tmem_ld32_nowait(taddr, v);
+          mbar_wait(&pempty_bar[sb], spar ^ 1u);
+          tmem_wait_ld();
+          if (pi == MT * NPANEL - 1) {       // accumulators read for the second time: release the buffer
+            tcgen05_fence_before();
+            mbar_arrive(&tempty_bar[buf]);
+          }
+          const float* prow = p.ws + p.ws_flag_words +
+                              ((long long)(wi.tile * (S - 1)) * BM + row) * BN + pn * PANEL_COLS + half * 32;
+          const uint32_t row_addr = smem_u32(sbuf) + (uint32_t)row * 128u;
+#pragma unroll
+          for (int k8 = 0; k8 < 4; ++k8) {               // 8 columns = one 16-byte staging store
+            float f[8];
+#pragma unroll
+            for (int h4 = 0; h4 < 2; ++h4) {             // 4-channel chunks never straddle a group
+              const int k = 2 * k8 + h4;
+              float x[4] = {__uint_as_float(v[4 * k]), __uint_as_float(v[4 * k + 1]), __uint_as_float(v[4 * k + 2]),
+                            __uint_as_float(v[4 * k + 3])};
+              if (S > 1) {                               // same order as pass 1: (partial 0 + partial 1 + ...) + own
+                float4 acc = __ldcg(reinterpret_cast<const float4*>(prow) + k);
+                for (int sp = 1; sp < S - 1; ++sp) {
+                  const float4 t4 = __ldcg(reinterpret_cast<const float4*>(prow + (long long)sp * BM * BN) + k);
+                  acc.x += t4.x; acc.y += t4.y; acc.z += t4.z; acc.w += t4.w;
+                }
+                x[0] = acc.x + x[0]; x[1] = acc.y + x[1]; x[2] = acc.z + x[2]; x[3] = acc.w + x[3];
+              }
+              float add[4] = {0.f, 0.f, 0.f, 0.f};
+              if (p.bias) {
+                const float4 t4 = __ldg(reinterpret_cast<const float4*>(p.bias + nc) + k);
+                add[0] = t4.x; add[1] = t4.y; add[2] = t4.z; add[3] = t4.w;
+              }
+              if (vrow) {
+                const float4 t4 = __ldg(reinterpret_cast<const float4*>(vrow + nc) + k);
+                add[0] += t4.x; add[1] += t4.y; add[2] += t4.z; add[3] += t4.w;
+              }
+              if (vrow2) {
+                const float4 t4 = __ldg(reinterpret_cast<const float4*>(vrow2 + nc) + k);
+                add[0] += t4.x; add[1] += t4.y; add[2] += t4.z; add[3] += t4.w;
+              }
+              const float2 mr = red[rb * NG + (nc + 4 * k) / gn_cg - g0];
+              const float4 g4 = __ldg(reinterpret_cast<const float4*>(p.gn_gamma + nc) + k);
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.gn_beta + nc) + k);
+              const float gg[4] = {g4.x, g4.y, g4.z, g4.w}, bt[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+              for (int jj = 0; jj < 4; ++jj) {
+                const float sc = mr.y * gg[jj];
+                // raw value = acc * alpha + add;  y = (raw - mean) * rstd * gamma + beta
+                f[4 * h4 + jj] = gn_act(x[jj], p.alpha * sc, fmaf(add[jj], sc, bt[jj] - mr.x * sc), gn_silu);
+              }
+            }
+            const bf16x8 pk = pack8_half(f);
+            const uint32_t dst = row_addr + (uint32_t)(((half * 4 + k8) ^ (row & 7)) << 4);   // SWIZZLE_128B
+            const uint4 u = *reinterpret_cast<const uint4*>(&pk);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(u.x), "r"(u.y), "r"(u.z), "r"(u.w)
+                         : "memory");
+          }
+          fence_proxy_async_smem();
+          mbar_arrive(&pfull_bar[sb]);
+        }
+        named_bar_sync(1, P_EPI_THREADS);      // red[] (the statistics table) is reused by the next tile's pass 1
+      }
       if (dbg != nullptr && et == 0 && j < 8) dbg[24 + j] = clock64();
     }
     if (p.stats != nullptr) {                    // flush the last panel's statistics
@@ -613,20 +852,30 @@ tapgemm_persist_kernel(const __grid_constant__ TapGemmParams p, const __grid_con
         if (wi.split < S - 1) continue;          // partial items store nothing
         const TileCoord c = decode_tile(p, wi.tile, tiles_m, tiles_n, BN, MT);
         const DevPhase& ph = p.phase[c.phase];
-        for (int pi = 0; pi < MT * NPANEL; ++pi, ++pc) {
-          const int m = pi / NPANEL, pn = pi - m * NPANEL;
-          const int n = c.n0 + pn * PANEL_COLS;
-          const int ty = c.ty * MT + m;
-          const uint32_t sb = pc & 1u, spar = (pc >> 1) & 1u;
-          const uint8_t* sbuf = staging + sb * PANEL_BYTES;
-          mbar_wait(&pfull_bar[sb], spar);
-          if (p.out_scale == 1)
-            tma_store_3d(&tmOut, sbuf, n, c.tx * p.bw, c.tb * p.bb * p.Hm + ty * p.bh);
-          else
-            tma_store_5d(&tmOut, sbuf, n, ph.px, c.tx * p.bw, ph.py, c.tb * p.bb * p.Hm + ty * p.bh);
-          bulk_commit_group();
-          bulk_wait_group_read<0>();             // shared memory has been read: the buffer is free again
-          mbar_arrive(&pempty_bar[sb]);
+        // pass 0: the raw tensor (skipped when only its GroupNorm is wanted); pass 1: the fused GroupNorm output
+        constexpr int npass = GN ? 2 : 1;
+        for (int pass = 0; pass < npass; ++pass) {
+          for (int pi = 0; pi < MT * NPANEL; ++pi, ++pc) {
+            const int m = pi / NPANEL, pn = pi - m * NPANEL;
+            const int n = c.n0 + pn * PANEL_COLS;
+            const int ty = c.ty * MT + m;
+            const uint32_t sb = pc & 1u, spar = (pc >> 1) & 1u;
+            const uint8_t* sbuf = staging + sb * PANEL_BYTES;
+            mbar_wait(&pfull_bar[sb], spar);
+            if (pass == 0 && p.gn_only) {        // staged only for the statistics
+              mbar_arrive(&pempty_bar[sb]);
+              continue;
+            }
+            if (pass == 1)
+              tma_store_3d(&tmGn, sbuf, n, c.tx * p.bw, c.tb * p.bb * p.Hm + ty * p.bh);
+            else if (p.out_scale == 1)
+              tma_store_3d(&tmOut, sbuf, n, c.tx * p.bw, c.tb * p.bb * p.Hm + ty * p.bh);
+            else
+              tma_store_5d(&tmOut, sbuf, n, ph.px, c.tx * p.bw, ph.py, c.tb * p.bb * p.Hm + ty * p.bh);
+            bulk_commit_group();
+            bulk_wait_group_read<0>();           // shared memory has been read: the buffer is free again
+            mbar_arrive(&pempty_bar[sb]);
+          }
         }
       }
       bulk_wait_group<0>();                      // all tensor stores complete before the CTA retires
@@ -682,6 +931,22 @@ int tapgemm_stats_parts(const its_conv_desc* d, const TapGemmParams& p) {
   return p.nphases * (p.bb == 1 ? p.tiles_x * p.tiles_y * (c.tm ? 2 : 1) : 1);
 }
 
+int tapgemm_gn_sync_words(const its_conv_desc* d, const TapGemmParams& p) {
+  if (p.nphases != 1 || p.out_scale != 1 || p.w_batch_stride != 0 || p.bb > 8) return -1;
+  if (p.gn_groups <= 0 || p.Cout % p.gn_groups != 0) return -1;
+  const int cg = p.Cout / p.gn_groups;
+  const PersistCfg c = persist_cfg(d, p);
+  // a group lies inside one N tile and a 4-channel statistics chunk inside one group; the (image, group) pairs of
+  // a tile share the 256 epilogue threads evenly (powers of two)
+  if (cg % 4 != 0 || c.bn % cg != 0) return -1;
+  const int pairs = p.bb * (c.bn / cg);
+  if (pairs > P_EPI_THREADS || (pairs & (pairs - 1)) != 0) return -1;
+  const int peers = p.tiles_x * (p.tiles_y / c.mt);
+  if (peers == 1) return 0;
+  if (peers > 64 || (peers & (peers - 1)) != 0) return -1;   // power of two: see gn_peer_rendezvous
+  return p.tiles_b * (p.Cout / c.bn);
+}
+
 bool tapgemm_persist_eligible(const its_conv_desc* d, const TapGemmParams& p) {
   if (p.out_fp32 || p.out_nchw || p.res != nullptr) return false;
   if (p.w_batch_stride != 0 && (p.bb != 1 || p.splits > 1)) return false;
@@ -693,12 +958,12 @@ bool tapgemm_persist_eligible(const its_conv_desc* d, const TapGemmParams& p) {
   return true;
 }
 
-template <int BN, int STAGES, int MT, int KS, bool TM, bool F16>
+template <int BN, int STAGES, int MT, int KS, bool TM, bool F16, bool GN>
 static int launch_persist_fmt(const TapGemmParams& p, const CUtensorMap* tmA, const CUtensorMap& tmB,
-                              const CUtensorMap& tmOut, cudaStream_t stream) {
+                              const CUtensorMap& tmOut, const CUtensorMap& tmGn, cudaStream_t stream) {
   using L = PersistSmem<BN, STAGES, MT, KS, TM>;
   static_assert(L::TOTAL <= 227 * 1024, "shared memory budget");
-  auto kern = tapgemm_persist_kernel<BN, STAGES, MT, KS, TM, F16>;
+  auto kern = tapgemm_persist_kernel<BN, STAGES, MT, KS, TM, F16, GN>;
   static PerDeviceBytes configured;
   if (configured.need(L::TOTAL))
     ITS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
@@ -714,7 +979,7 @@ static int launch_persist_fmt(const TapGemmParams& p, const CUtensorMap* tmA, co
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled(1) ? 1 : 0;
-  ITS_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, p, tmA[0], tmA[1], tmA[2], tmB, tmOut));
+  ITS_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, p, tmA[0], tmA[1], tmA[2], tmB, tmOut, tmGn));
   return ITS_OK;
 }
 
@@ -722,9 +987,14 @@ static int launch_persist_fmt(const TapGemmParams& p, const CUtensorMap* tmA, co
 // the unrolled epilogue loops cost 1.3-1.8 % of a config-A pass (measured)
 template <int BN, int STAGES, int MT, int KS, bool TM = false>
 static int launch_persist(const TapGemmParams& p, const CUtensorMap* tmA, const CUtensorMap& tmB,
-                          const CUtensorMap& tmOut, cudaStream_t stream) {
-  if (p.out_fp16) return launch_persist_fmt<BN, STAGES, MT, KS, TM, true>(p, tmA, tmB, tmOut, stream);
-  return launch_persist_fmt<BN, STAGES, MT, KS, TM, false>(p, tmA, tmB, tmOut, stream);
+                          const CUtensorMap& tmOut, const CUtensorMap& tmGn, cudaStream_t stream) {
+  // ... and so is the fused GroupNorm pass: the plain epilogue keeps its register allocation
+  if (p.gn_out != nullptr) {
+    if (p.out_fp16) return launch_persist_fmt<BN, STAGES, MT, KS, TM, true, true>(p, tmA, tmB, tmOut, tmGn, stream);
+    return launch_persist_fmt<BN, STAGES, MT, KS, TM, false, true>(p, tmA, tmB, tmOut, tmGn, stream);
+  }
+  if (p.out_fp16) return launch_persist_fmt<BN, STAGES, MT, KS, TM, true, false>(p, tmA, tmB, tmOut, tmGn, stream);
+  return launch_persist_fmt<BN, STAGES, MT, KS, TM, false, false>(p, tmA, tmB, tmOut, tmGn, stream);
 }
 
 int tapgemm_launch_persist(const its_conv_desc* d, const TapGemmParams& p, cudaStream_t stream) {
@@ -754,7 +1024,19 @@ int tapgemm_launch_persist(const its_conv_desc* d, const TapGemmParams& p, cudaS
     // items never wait, hence every owner's spin terminates whatever the number of rounds.
     pp.ws_flag_words = (int)nflag;
   }
-  CUtensorMap tmA[ITS_MAX_SRC], tmB, tmOut;
+  if (p.gn_out != nullptr) {
+    const int words = tapgemm_gn_sync_words(d, p);
+    ITS_REQUIRE(words >= 0, "its_conv_igemm: this layer's GroupNorm cannot be fused into its epilogue "
+                "(its_conv_gn_sync_words() < 0): Cout=%d groups=%d bn=%d", p.Cout, p.gn_groups, bn);
+    ITS_REQUIRE(p.stats != nullptr, "its_conv_igemm: the fused GroupNorm epilogue needs the statistics array");
+    ITS_REQUIRE(p.gn_gamma != nullptr && p.gn_beta != nullptr, "its_conv_igemm: gn_gamma / gn_beta");
+    ITS_REQUIRE(words == 0 || p.gn_sync != nullptr, "its_conv_igemm: gn_sync needs %d zero-initialised ints", words);
+    ITS_REQUIRE(p.gn_c_pitch >= p.Cout && p.gn_c_pitch % 8 == 0 && (reinterpret_cast<uintptr_t>(p.gn_out) & 15) == 0,
+                "its_conv_igemm: gn_out pitch / alignment");
+    pp.gn_sync_words = words;
+    pp.gn_peers = p.tiles_x * (p.tiles_y / mt);
+  }
+  CUtensorMap tmA[ITS_MAX_SRC], tmB, tmOut, tmGn;
   int rc = tapgemm_encode_operand_maps(p, bn, tmA, &tmB, mt);
   if (rc != ITS_OK) return rc;
   const cuuint64_t pitch_b = (cuuint64_t)p.out_c_pitch * 2;
@@ -776,25 +1058,35 @@ int tapgemm_launch_persist(const its_conv_desc* d, const TapGemmParams& p, cudaS
     rc = encode_bf16_map(&tmOut, 5, p.out, dims, strides, box, estr, "output");
   }
   if (rc != ITS_OK) return rc;
+  tmGn = tmOut;
+  if (p.gn_out != nullptr) {
+    const cuuint64_t gpitch = (cuuint64_t)p.gn_c_pitch * 2;
+    const cuuint64_t dims[3] = {(cuuint64_t)p.Cout, (cuuint64_t)p.Wm, (cuuint64_t)p.B * p.Hm};
+    const cuuint64_t strides[2] = {gpitch, gpitch * p.Wm};
+    const cuuint32_t box[3] = {(cuuint32_t)PANEL_COLS, (cuuint32_t)p.bw, (cuuint32_t)(p.bh * p.bb)};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    rc = encode_bf16_map(&tmGn, 3, p.gn_out, dims, strides, box, estr, "fused GroupNorm output");
+    if (rc != ITS_OK) return rc;
+  }
   // two k-blocks per ring stage when every tap, split and format switch covers whole pairs
   bool pairs = (mt == 1 && bn <= 128 && d->cluster != 3);
   for (int s = 0; s < p.nsrc && pairs; ++s) pairs = (p.src[s].C % (2 * BK) == 0);
   for (int f = 0; f < p.nphases && pairs; ++f)
     pairs = (p.phase[f].nkb % (2 * p.splits) == 0) && (p.phase[f].kb_switch % 2 == 0);
   if (mt == 2) {
-    if (bn == 64) return launch_persist<64, 4, 2, 1>(pp, tmA, tmB, tmOut, stream);
-    if (cfg.tm) return launch_persist<128, 4, 2, 1, true>(pp, tmA, tmB, tmOut, stream);
-    return launch_persist<128, 4, 2, 1>(pp, tmA, tmB, tmOut, stream);
+    if (bn == 64) return launch_persist<64, 4, 2, 1>(pp, tmA, tmB, tmOut, tmGn, stream);
+    if (cfg.tm) return launch_persist<128, 4, 2, 1, true>(pp, tmA, tmB, tmOut, tmGn, stream);
+    return launch_persist<128, 4, 2, 1>(pp, tmA, tmB, tmOut, tmGn, stream);
   }
   if (pairs) {
-    if (bn == 64) return launch_persist<64, 4, 1, 2>(pp, tmA, tmB, tmOut, stream);
-    return launch_persist<128, 3, 1, 2>(pp, tmA, tmB, tmOut, stream);
+    if (bn == 64) return launch_persist<64, 4, 1, 2>(pp, tmA, tmB, tmOut, tmGn, stream);
+    return launch_persist<128, 3, 1, 2>(pp, tmA, tmB, tmOut, tmGn, stream);
   }
   switch (bn) {
-    case 64:  return launch_persist<64, 8, 1, 1>(pp, tmA, tmB, tmOut, stream);
-    case 128: return launch_persist<128, 6, 1, 1>(pp, tmA, tmB, tmOut, stream);
-    case 192: return launch_persist<192, 4, 1, 1>(pp, tmA, tmB, tmOut, stream);
-    default:  return launch_persist<256, 4, 1, 1>(pp, tmA, tmB, tmOut, stream);
+    case 64:  return launch_persist<64, 8, 1, 1>(pp, tmA, tmB, tmOut, tmGn, stream);
+    case 128: return launch_persist<128, 6, 1, 1>(pp, tmA, tmB, tmOut, tmGn, stream);
+    case 192: return launch_persist<192, 4, 1, 1>(pp, tmA, tmB, tmOut, tmGn, stream);
+    default:  return launch_persist<256, 4, 1, 1>(pp, tmA, tmB, tmOut, tmGn, stream);
   }
 }
 

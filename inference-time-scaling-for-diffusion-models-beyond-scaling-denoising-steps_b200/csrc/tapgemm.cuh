@@ -48,6 +48,17 @@ struct TapGemmParams {
   int stats_parts;
   int out_fp16;              // 16-bit output format: 0 = bf16, 1 = IEEE fp16
   int res_fp16;              // format of the residual tensor read by the non-folded epilogues
+  // GroupNorm(+Swish) of this launch's own output fused into the persistent kernel's epilogue
+  void* gn_out;              // IEEE fp16 NHWC, or null
+  int gn_c_pitch;
+  const float* gn_gamma;
+  const float* gn_beta;
+  int gn_groups;
+  float gn_eps;
+  int gn_silu, gn_only;
+  int* gn_sync;              // [gn_sync_words] monotonic arrival counters of the peer tiles of an image
+  int gn_sync_words;
+  int gn_peers;              // tiles an image spans (same N tile); 1 = a tile holds whole images
   // M tiling: a 128-row tile is a (bb images) x (bh rows) x (bw cols) box
   int bw, bh, bb, tiles_x, tiles_y, tiles_b;
 };
@@ -61,6 +72,8 @@ bool tapgemm_persist_eligible(const its_conv_desc* d, const TapGemmParams& p);
 int tapgemm_launch_persist(const its_conv_desc* d, const TapGemmParams& p, cudaStream_t stream);
 // number of GroupNorm partial-sum slots per image the persistent kernel writes for this tiling
 int tapgemm_stats_parts(const its_conv_desc* d, const TapGemmParams& p);
+// peer-tile counters the fused GroupNorm epilogue needs for this tiling (-1 = not fusable, see its_b200.h)
+int tapgemm_gn_sync_words(const its_conv_desc* d, const TapGemmParams& p);
 int encode_bf16_map(CUtensorMap* tm, int rank, const void* base, const cuuint64_t* dims,
                     const cuuint64_t* strides_bytes, const cuuint32_t* box, const cuuint32_t* estr,
                     const char* what);

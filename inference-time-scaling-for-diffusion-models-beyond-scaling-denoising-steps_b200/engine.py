@@ -98,6 +98,7 @@ class UNetPlan:
         self.fork_time_chain, self._side = False, None
         self.res_dtype = FP16 if (_os.environ.get("ITS_RESIDUAL_FP16", "0") == "1" and impl is None) else BF16
         self.gn_dtype = FP16 if (FP16_GN and impl != 1) else BF16
+        self.prefused, self.gn_fusion, self.n_gn_fused = {}, _os.environ.get("ITS_GN_FUSION", "1") != "0", 0
         return self
 
     # ------------------------------------------------------------ buffers --
@@ -171,20 +172,25 @@ class UNetPlan:
     _T_KB = {256: 290.0, 192: 250.0, 128: 215.0, 64: 175.0}
     _T_SPLIT2 = 5000.0      # publish + re-read of the fp32 partial through L2, flag round trip
 
-    def _persist_plan(self, Hm, Wm, cout, nphases, nkb) -> Tuple[int, int]:
+    # N tiles that may split K inside the launch (ITS_SPLIT_BNS overrides, for measurements)
+    _SPLIT_BNS = tuple(int(x) for x in _os.environ.get("ITS_SPLIT_BNS", "64").split(","))
+
+    def _persist_plan(self, Hm, Wm, cout, nphases, nkb, group_width: int = 0) -> Tuple[int, int]:
         """(N tile, split-K factor) of a layer on the persistent schedule, from the layer shape at the
-        design batch only (so that the fp32 summation order never depends on the actual batch)."""
+        design batch only (so that the fp32 summation order never depends on the actual batch).
+        group_width > 0: the layer's own GroupNorm is to be fused into its epilogue, so a group must lie
+        inside one N tile (its_conv_gn_sync_words); (0, 0) when no N tile allows that."""
         bw, bh, bb = self._box(Hm, Wm)
         tiles_y = -(-Hm // bh)
         tiles_m = self._tiles_at(self.DESIGN_BATCH, Hm, Wm)
         best = None
         for bn in (256, 192, 128, 64):
-            if cout % bn:
+            if cout % bn or (group_width and bn % group_width):
                 continue
             tiles = tiles_m * (cout // bn) * nphases
             two_rows = bn <= 128 and bb == 1 and tiles_y % 2 == 0
             for S in (1, 2):
-                if S > 1 and (bn != 64 or nkb < 16 or tiles * S > self.sm_count or two_rows):
+                if S > 1 and (bn not in self._SPLIT_BNS or nkb < 16 or tiles * S > self.sm_count or two_rows):
                     break
                 if two_rows:                # two row boxes share each weight tile (measured ~410 ns per pair)
                     rounds = -(-(tiles // 2) // self.sm_count)
@@ -196,13 +202,21 @@ class UNetPlan:
                     t += self._T_SPLIT2
                 if best is None or t < best[0] - 1e-9:
                     best = (t, bn, S)
+        if best is None:
+            return 0, 0
         return best[1], best[2]
 
     def conv(self, srcs, phases, Hm, Wm, w, cout, *, out=None, out_scale=1, bias=None, vec=None,
              vec_off=0, vec2=None, vec2_off=0, res=None, alpha=1.0, out_fp32=False, w_batch_stride=0,
-             w_pitch=None, B=None, out_shape=None, out_nchw=False, want_stats=True, out_dtype=None) -> torch.Tensor:
+             w_pitch=None, B=None, out_shape=None, out_nchw=False, want_stats=True, out_dtype=None,
+             fuse_gn=None, gn_only=False) -> torch.Tensor:
         """Append one tap-GEMM launch.  srcs: list of (tensor NHWC, C_used, c_off, stride, bcast);
-        phases: list of (taps[(src,dy,dx)], w_k0, py, px)."""
+        phases: list of (taps[(src,dy,dx)], w_k0, py, px).
+        fuse_gn = (GroupNorm module, silu): the GroupNorm(+Swish) that the consumer of this tensor opens with is
+        applied by this launch's own epilogue when the tiling allows it (its_conv_gn_sync_words); group_norm()
+        then finds the normalised tensor instead of launching.  gn_only: nobody reads the raw tensor (a
+        ResBlock's conv1 output feeds block2's GroupNorm only) — it is then not stored at all and the
+        normalised tensor is returned in its place."""
         B = self.n_img if B is None else B
         d = ConvDesc()
         d.nsrc = len(srcs)
@@ -249,8 +263,16 @@ class UNetPlan:
             d.res = None
         persistent = impl == 0 and self.L.its_conv_stats_parts(C.byref(d)) > 0
         bn, splits = 0, 1
+        want_fuse = (fuse_gn is not None and persistent and self.gn_fusion and want_stats and self.gn_dtype == FP16
+                     and len(phases) == 1 and out_scale == 1 and cout % fuse_gn[0].num_groups == 0)
         if persistent and self.split_k:
-            bn, splits = self._persist_plan(Hm, Wm, cout, len(phases), nkb_min + (cout // 64 if can_fold else 0))
+            nkb_plan = nkb_min + (cout // 64 if can_fold else 0)
+            bn, splits = 0, 0
+            if want_fuse:
+                bn, splits = self._persist_plan(Hm, Wm, cout, len(phases), nkb_plan, cout // fuse_gn[0].num_groups)
+            if bn == 0:
+                want_fuse = False
+                bn, splits = self._persist_plan(Hm, Wm, cout, len(phases), nkb_plan)
         if persistent:
             if can_fold:
                 # identity shortcut as one more K block with identity weights (exact: 1.0 * bf16 value
@@ -282,6 +304,32 @@ class UNetPlan:
                 st = self._new((B, parts, cout // 4, 2), torch.float32)
                 d.stats, d.stats_parts = st.data_ptr(), parts
                 self.stats_of[out.data_ptr()] = (st, parts)
+            if want_fuse:
+                gnm, gn_silu = fuse_gn
+                d.gn_groups = gnm.num_groups
+                words = self.L.its_conv_gn_sync_words(C.byref(d))
+                if words < 0:
+                    d.gn_groups = 0
+                else:
+                    gn_out = self._new((B, Hout, Wout, cout), FP16)
+                    gamma, beta = self._hold(gnm.weight, torch.float32), self._hold(gnm.bias, torch.float32)
+                    d.gn_out, d.gn_c_pitch = gn_out.data_ptr(), cout
+                    d.gn_gamma, d.gn_beta, d.gn_eps = gamma.data_ptr(), beta.data_ptr(), float(gnm.eps)
+                    d.gn_silu, d.gn_only = int(gn_silu), int(bool(gn_only))
+                    if words > 0:
+                        # arrival counters of the tiles an image spans (monotonic: zeroed once, here)
+                        sync = torch.zeros(words, dtype=torch.int32, device=self.dev)
+                        self.keep.append(sync)
+                        d.gn_sync = sync.data_ptr()
+                    self.n_gn_fused += 1
+                    if gn_only:
+                        # the raw tensor is never stored: drop its buffer, the map is encoded over gn_out
+                        self.keep = [t for t in self.keep if t is not out]
+                        self.stats_of.pop(out.data_ptr(), None)
+                        d.out, d.out_c_pitch = gn_out.data_ptr(), cout
+                        d.out_fp16 = (d.out_fp16 & ~1) | 1
+                        out = gn_out
+                    self.prefused[(out.data_ptr(), id(gnm))] = (gn_out, bool(gn_silu))
         else:
             if res is not None:
                 d.res = res.data_ptr()
@@ -315,6 +363,12 @@ class UNetPlan:
         return out
 
     def group_norm(self, srcs: Sequence[torch.Tensor], gn, silu: bool) -> torch.Tensor:
+        if len(srcs) == 1:
+            pre = self.prefused.get((srcs[0].data_ptr(), id(gn)))
+            if pre is not None:       # already applied by the epilogue of the launch that produced srcs[0]
+                if pre[1] != bool(silu):
+                    raise RuntimeError("fused GroupNorm was built with a different activation")
+                return pre[0]
         x0 = srcs[0]
         x1 = srcs[1] if len(srcs) > 1 else None
         B, H, W, C0 = x0.shape
@@ -362,7 +416,7 @@ class UNetPlan:
         return y
 
     # ------------------------------------------------------------- blocks --
-    def _res_block(self, rb, xs: List[torch.Tensor], proj_off: int) -> torch.Tensor:
+    def _res_block(self, rb, xs: List[torch.Tensor], proj_off: int, next_gn=None) -> torch.Tensor:
         B, H, W = xs[0].shape[:3]
         cin = sum(t.shape[-1] for t in xs)
         cout = rb.block1[2].out_channels
@@ -370,8 +424,11 @@ class UNetPlan:
         w1 = self._hold(pack_conv_weight(rb.block1[2].weight), torch.float32)
         b1 = self._hold(rb.block1[2].bias, torch.float32)
         h1 = self.conv([(a1, cin, 0, 1, False)], [(taps_square(3), 0, 0, 0)], H, W, w1, cout, bias=b1,
-                       vec=self.tproj, vec_off=proj_off, vec2=self.cproj, vec2_off=proj_off, out_dtype=self.res_dtype)
+                       vec=self.tproj, vec_off=proj_off, vec2=self.cproj, vec2_off=proj_off, out_dtype=self.res_dtype,
+                       fuse_gn=(rb.block2[0], True), gn_only=True)
         a2 = self.group_norm([h1], rb.block2[0], silu=True)
+        has_attn = not isinstance(rb.attn, torch.nn.Identity)
+        gn_after = (rb.attn.group_norm, False) if has_attn else next_gn   # what reads this block's conv2 output
         conv2 = rb.block2[3]
         w2 = pack_conv_weight(conv2.weight)
         b2 = conv2.bias.detach().float()
@@ -382,19 +439,20 @@ class UNetPlan:
             b2 = self._hold(b2 + rb.shortcut.bias.detach().float(), torch.float32)
             srcs = [(a2, cout, 0, 1, False)] + [(t, t.shape[-1], 0, 1, False) for t in xs]
             taps = taps_square(3) + [(1 + i, 0, 0) for i in range(len(xs))]
-            h2 = self.conv(srcs, [(taps, 0, 0, 0)], H, W, w2, cout, bias=b2, out_dtype=self.res_dtype)
+            h2 = self.conv(srcs, [(taps, 0, 0, 0)], H, W, w2, cout, bias=b2, out_dtype=self.res_dtype,
+                           fuse_gn=gn_after)
         else:
             if len(xs) != 1:
                 raise RuntimeError("identity shortcut over a concatenated input is not supported")
             w2 = self._hold(w2, torch.float32)
             b2 = self._hold(b2, torch.float32)
             h2 = self.conv([(a2, cout, 0, 1, False)], [(taps_square(3), 0, 0, 0)], H, W, w2, cout, bias=b2,
-                           res=xs[0], out_dtype=self.res_dtype)
-        if not isinstance(rb.attn, torch.nn.Identity):
-            h2 = self._attn_block(rb.attn, h2)
+                           res=xs[0], out_dtype=self.res_dtype, fuse_gn=gn_after)
+        if has_attn:
+            h2 = self._attn_block(rb.attn, h2, next_gn)
         return h2
 
-    def _attn_block(self, at, x: torch.Tensor) -> torch.Tensor:
+    def _attn_block(self, at, x: torch.Tensor, next_gn=None) -> torch.Tensor:
         B, H, W, Cc = x.shape
         N = H * W
         scale = float(int(Cc) ** (-0.5))
@@ -419,7 +477,8 @@ class UNetPlan:
                          kind="attention_fused" if fused256 else "attention_flash")
                 wp = self._hold(at.proj.weight.detach().float()[:, :, 0, 0], torch.float32)
                 bp = self._hold(at.proj.bias, torch.float32)
-                return self.conv([(o, Cc, 0, 1, False)], [(one, 0, 0, 0)], H, W, wp, Cc, bias=bp, res=x, out_dtype=self.res_dtype)
+                return self.conv([(o, Cc, 0, 1, False)], [(one, 0, 0, 0)], H, W, wp, Cc, bias=bp, res=x, out_dtype=self.res_dtype,
+                                 fuse_gn=next_gn)
             wqk = self._hold(torch.cat([wq, wk], 0), torch.float32)
             bqk = self._hold(torch.cat([bq, bk], 0), torch.float32)
             qk = self.conv([(a, Cc, 0, 1, False)], [(one, 0, 0, 0)], H, W, wqk, 2 * Cc, bias=bqk, want_stats=False)
@@ -436,7 +495,8 @@ class UNetPlan:
                          kind="attention_fused" if fused256 else "attention_flash")
                 wp = self._hold(at.proj.weight.detach().float()[:, :, 0, 0], torch.float32)
                 bp = self._hold(at.proj.bias, torch.float32)
-                return self.conv([(o, Cc, 0, 1, False)], [(one, 0, 0, 0)], H, W, wp, Cc, bias=bp, res=x, out_dtype=self.res_dtype)
+                return self.conv([(o, Cc, 0, 1, False)], [(one, 0, 0, 0)], H, W, wp, Cc, bias=bp, res=x, out_dtype=self.res_dtype,
+                                 fuse_gn=next_gn)
             # S = scale * Q K^T (fp32), per image
             k_view = qk.view(B, N, 2 * Cc)[:, :, Cc:]
             S = self.conv([(qk, Cc, 0, 1, False)], [(one, 0, 0, 0)], H, W, k_view, N, alpha=scale,
@@ -468,9 +528,10 @@ class UNetPlan:
                      flops=4 * B * N * N * Cc, kind="attention_small")
         wp = self._hold(at.proj.weight.detach().float()[:, :, 0, 0], torch.float32)
         bp = self._hold(at.proj.bias, torch.float32)
-        return self.conv([(o, Cc, 0, 1, False)], [(one, 0, 0, 0)], H, W, wp, Cc, bias=bp, res=x, out_dtype=self.res_dtype)
+        return self.conv([(o, Cc, 0, 1, False)], [(one, 0, 0, 0)], H, W, wp, Cc, bias=bp, res=x, out_dtype=self.res_dtype,
+                                 fuse_gn=next_gn)
 
-    def _down(self, ds, x: torch.Tensor) -> torch.Tensor:
+    def _down(self, ds, x: torch.Tensor, next_gn=None) -> torch.Tensor:
         B, H, W, Cc = x.shape
         if hasattr(ds, "main"):       # Model.py:96-108
             w = self._hold(pack_conv_weight(ds.main.weight), torch.float32)
@@ -480,7 +541,8 @@ class UNetPlan:
             w = self._hold(torch.cat([pack_conv_weight(ds.c1.weight), pack_conv_weight(ds.c2.weight)], 1), torch.float32)
             b = self._hold(ds.c1.bias.detach().float() + ds.c2.bias.detach().float(), torch.float32)
             taps = taps_square(3) + taps_square(5)
-        return self.conv([(x, Cc, 0, 2, False)], [(taps, 0, 0, 0)], H // 2, W // 2, w, Cc, bias=b, out_dtype=self.res_dtype)
+        return self.conv([(x, Cc, 0, 2, False)], [(taps, 0, 0, 0)], H // 2, W // 2, w, Cc, bias=b, out_dtype=self.res_dtype,
+                         fuse_gn=next_gn)
 
     def _up(self, us, x: torch.Tensor) -> torch.Tensor:
         B, H, W, Cc = x.shape
@@ -523,7 +585,7 @@ class UNetPlan:
         return self.conv([(y, Cc, 0, 1, False)], [(taps_square(3), 0, 0, 0)], 2 * H, 2 * W, wc, Cc, bias=bc,
                          out_dtype=self.res_dtype)
 
-    def head_conv(self, weight, bias, x_in: torch.Tensor, B: int, H: int, W: int) -> torch.Tensor:
+    def head_conv(self, weight, bias, x_in: torch.Tensor, B: int, H: int, W: int, next_gn=None) -> torch.Tensor:
         """Model.py:269: conv3x3(3 -> ch) of the NCHW fp32 sampler state into NHWC bf16."""
         L = self.L
         ch = weight.shape[0]
@@ -540,7 +602,7 @@ class UNetPlan:
             wpk = torch.zeros(ch, 128, device=w32.device)
             wpk[:, 0:27], wpk[:, 27:54], wpk[:, 54:81] = w_hi, w_hi, w32 - w_hi
             h = self.conv([(patches, 128, 0, 1, False)], [([(0, 0, 0)], 0, 0, 0)], H, W, self._hold(wpk, BF16), ch,
-                          bias=hb, B=B, out_dtype=self.res_dtype)
+                          bias=hb, B=B, out_dtype=self.res_dtype, fuse_gn=next_gn)
             self.flops -= 2 * B * H * W * ch * (128 - 27)     # algorithmic work is the 27-tap convolution
             return h
         h = self._new((B, H, W, ch))
@@ -559,8 +621,11 @@ class UNetPlan:
         self.stats_of, self.schedule, self.fold_residual = {}, 0, True
         self.ws_persist, self.sm_count, self.fused_attention = None, 148, True
         self.head_on_tensor_cores = True
+        # GroupNorm(+Swish) applied by the epilogue of the convolution that produces its input (ITS_GN_FUSION=0:
+        # every GroupNorm as its own its_group_norm_apply launch, the round-1 plan)
+        self.prefused, self.n_gn_fused = {}, 0
+        self.gn_fusion = _os.environ.get("ITS_GN_FUSION", "1") != "0" and self.impl_forced is None
         # debugging switches (tests/parity triage): fall back to the simpler schedule of a stage
-        import os as _os
         self.schedule = int(_os.environ.get("ITS_SCHEDULE", "0"))
         self.fused_attention = _os.environ.get("ITS_FUSED_ATTENTION", "1") != "0"
         self.head_on_tensor_cores = _os.environ.get("ITS_HEAD_TC", "1") != "0"
@@ -628,16 +693,30 @@ class UNetPlan:
             self.cproj = self.linear(cemb, wc, bc, silu_in=True)
             self._into_label_ops = False
         # ---- head
-        h = self.head_conv(m.head.weight, m.head.bias, self.x_in, B, H, W)
+        # The GroupNorm -> Swish that the NEXT layer opens with, when that layer reads this layer's output alone
+        # (down path, middle, tail): the producing launch applies it in its epilogue.  Up-path ResBlocks
+        # normalise the concatenation [h, skip] (their groups mix both tensors) and resampling convs read
+        # the raw tensor: no fusion there.
+        seq = list(m.downblocks) + list(m.middleblocks)
+
+        def opens_with(layer):
+            return (layer.block1[0], True) if hasattr(layer, "temb_proj") else None
+
+        nxt = {id(a): opens_with(b) for a, b in zip(seq[:-1], seq[1:])}
+        ups = list(m.upblocks)
+        h = self.head_conv(m.head.weight, m.head.bias, self.x_in, B, H, W, next_gn=opens_with(seq[0]))
         hs = [h]
         for layer in m.downblocks:
-            h = self._res_block(layer, [h], offs[id(layer)]) if hasattr(layer, "temb_proj") else self._down(layer, h)
+            if hasattr(layer, "temb_proj"):
+                h = self._res_block(layer, [h], offs[id(layer)], nxt.get(id(layer)))
+            else:
+                h = self._down(layer, h, nxt.get(id(layer)))
             hs.append(h)
         for layer in m.middleblocks:
-            h = self._res_block(layer, [h], offs[id(layer)])
-        for layer in m.upblocks:
+            h = self._res_block(layer, [h], offs[id(layer)], nxt.get(id(layer)))
+        for i, layer in enumerate(ups):
             if hasattr(layer, "temb_proj"):
-                h = self._res_block(layer, [h, hs.pop()], offs[id(layer)])
+                h = self._res_block(layer, [h, hs.pop()], offs[id(layer)], (m.tail[0], True) if i == len(ups) - 1 else None)
             else:
                 h = self._up(layer, h)
         assert len(hs) == 0

@@ -306,6 +306,110 @@ def test_persistent_conv_statistics_feed_group_norm(cuda_dev, built_lib, B, H, C
         ref = ref * torch.sigmoid(ref)
     check_close(nchw(y), ref, 6e-3, "group_norm_apply")
 
+FUSED_GN_SHAPES = [
+    # B, H, Cin, Cout, silu, gn_only, extras
+    (8, 4, 512, 512, True, True, False),      # 4x4: eight whole images per tile, split-K owner re-reads its partial
+    (19, 4, 256, 512, True, False, True),     # ragged last tile, raw + normalised output
+    (4, 8, 128, 384, True, True, True),       # 8x8: two images per tile, 12-channel groups inside a 192-wide N tile
+    (5, 8, 384, 256, False, False, False),    # no Swish (the attention block's GroupNorm)
+    (3, 16, 128, 256, True, True, True),      # 16x16: an image = 2 tiles, peer rendezvous
+    (2, 16, 64, 128, True, False, False),     # 16x16, 128 channels: two row boxes per tile (MT = 2, transposed accumulator)
+    (3, 32, 128, 128, True, True, True),      # 32x32 transposed-accumulator mode: 4 peer tiles per image
+    (50, 32, 64, 128, True, False, True),     # 200 tiles on 148 CTAs: peers straddle the round boundary
+    (1, 64, 64, 128, True, True, False),      # 64x64: 16 peer tiles
+    (2, 32, 128, 256, False, False, False),   # 32x32 with a 256-wide tile: 8 peers
+]
+
+
+@pytest.mark.parametrize("B,H,Cin,Cout,silu,gn_only,extras", FUSED_GN_SHAPES)
+def test_conv_with_fused_group_norm_epilogue(cuda_dev, built_lib, B, H, Cin, Cout, silu, gn_only, extras):
+    """GroupNorm(32, Cout) (+ Swish) of a convolution's output applied by that launch's own epilogue
+    (its_conv_desc.gn_out; Model.py:186-190 reads exactly what Model.py:173 wrote) against nn.GroupNorm on the
+    fp32 convolution: whole-image tiles, peer-tile rendezvous, transposed accumulators, split-K, raw + normalised
+    or normalised only.  The launch must replace the stand-alone GroupNorm launch, and repeated launches (graph
+    replay) must find the rendezvous counters zero again."""
+    from its_b200.engine import UNetPlan, pack_conv_weight, taps_square
+    dev = cuda_dev
+    g = torch.Generator().manual_seed(B * 1000 + H * 10 + Cout)
+    x = (torch.randn(B, Cin, H, H, generator=g) * 1.3 + 0.2).to(dev)
+    w = (torch.randn(Cout, Cin, 3, 3, generator=g) / math.sqrt(Cin * 9)).to(dev)
+    bias = torch.randn(Cout, generator=g).to(dev)
+    gn = torch.nn.GroupNorm(32, Cout).to(dev)
+    with torch.no_grad():
+        gn.weight.copy_(1 + 0.3 * torch.randn(Cout, generator=g))
+        gn.bias.copy_(0.2 * torch.randn(Cout, generator=g))
+    plan = UNetPlan.scratch(dev, B, 0)
+    kw = {}
+    ref = F.conv2d(bf(x), bf(w), bias, padding=1)
+    if extras:
+        vec = torch.randn(B, Cout + 8, generator=g).to(dev)
+        vec2 = torch.randn(1, Cout, generator=g).to(dev)
+        kw = dict(vec=vec, vec_off=8, vec2=vec2)
+        ref = ref + vec[:, 8:].view(B, Cout, 1, 1) + vec2.view(1, Cout, 1, 1)
+    wp = pack_conv_weight(w).contiguous()
+    xin = nhwc(x)                          # the plan borrows the pointer: keep the tensor alive
+    out = plan.conv([(xin, Cin, 0, 1, False)], [(taps_square(3), 0, 0, 0)], H, H, wp, Cout, bias=bias,
+                    fuse_gn=(gn, silu), gn_only=gn_only, **kw)
+    assert plan.n_gn_fused == 1, "the layer was expected to be fusable"
+    y = plan.group_norm([out], gn, silu)
+    assert len(plan.ops) == 1 and plan.op_info[-1][0] == "tapgemm_sm100"     # no GroupNorm launch was appended
+    with torch.no_grad():
+        want = gn(ref)
+        if silu:
+            want = want * torch.sigmoid(want)
+    for rep in range(3):                   # repeated launches: the rendezvous counters keep counting
+        y.zero_()
+        plan.run()
+        torch.cuda.synchronize()
+        got = nchw(y)
+        bad = ~torch.isfinite(got) | ((got - want).abs() > 8e-3 * want.abs().max())
+        if bad.any():          # say where: images / 64-channel tiles that are wrong
+            imgs = sorted(set(bad.nonzero()[:, 0].tolist()))
+            tiles = sorted(set((bad.nonzero()[:, 1] // 64).tolist()))
+            print(f"launch {rep}: {int(bad.sum())} bad of {bad.numel()}, nan {int((~torch.isfinite(got)).sum())}, "
+                  f"zeros among bad {int((got[bad] == 0).sum())}, images {imgs[:8]}, channel tiles {tiles}")
+        check_close(got, want, 8e-3, f"fused GroupNorm output, launch {rep}")
+    assert y.dtype == torch.float16
+    if gn_only:
+        assert out is y                    # the raw tensor is not materialised
+    else:
+        check_close(nchw(out), ref, 6e-3, "raw output")
+        # the statistics by-product still serves later consumers of the raw tensor (skip connections)
+        st, parts = plan.stats_of[out.data_ptr()]
+        v = out.float()
+        ref_s = v.reshape(B, -1, Cout // 4, 4).sum((1, 3))
+        assert (st[..., 0].sum(1) - ref_s).abs().max().item() <= 2e-3 * max(1.0, ref_s.abs().max().item())
+    for t in plan.keep:                    # every rendezvous counter saw all its peer tiles in each of the 3 launches
+        if t.dtype == torch.int32:
+            assert int(t.min().item()) == int(t.max().item()) and int(t[0].item()) % 3 == 0 and int(t[0].item()) > 0
+
+
+def test_fused_group_norm_matches_the_two_launch_plan(cuda_dev, built_lib):
+    """The same ResBlock-shaped chain built with and without the fused epilogue (ITS_GN_FUSION): the second conv's
+    output agrees to the rounding of the 16-bit intermediate the fusion removes."""
+    from its_b200.engine import UNetPlan, pack_conv_weight, taps_square
+    dev = cuda_dev
+    B, H, Cc = 6, 16, 256
+    g = torch.Generator().manual_seed(77)
+    x = torch.randn(B, Cc, H, H, generator=g).to(dev)
+    w1 = (torch.randn(Cc, Cc, 3, 3, generator=g) / math.sqrt(Cc * 9)).to(dev)
+    w2 = (torch.randn(Cc, Cc, 3, 3, generator=g) / math.sqrt(Cc * 9)).to(dev)
+    gn = torch.nn.GroupNorm(32, Cc).to(dev)
+    outs, xin = {}, nhwc(x)
+    for fused in (False, True):
+        plan = UNetPlan.scratch(dev, B, 0)
+        plan.gn_fusion = fused
+        h1 = plan.conv([(xin, Cc, 0, 1, False)], [(taps_square(3), 0, 0, 0)], H, H, pack_conv_weight(w1).contiguous(),
+                       Cc, fuse_gn=(gn, True), gn_only=True)
+        a2 = plan.group_norm([h1], gn, True)
+        h2 = plan.conv([(a2, Cc, 0, 1, False)], [(taps_square(3), 0, 0, 0)], H, H, pack_conv_weight(w2).contiguous(), Cc)
+        assert len(plan.ops) == (2 if fused else 3)
+        plan.run()
+        torch.cuda.synchronize()
+        outs[fused] = nchw(h2)
+    check_close(outs[True], outs[False], 6e-3, "fused vs two-launch chain")
+
+
 @pytest.mark.parametrize("impl", [1, 0], ids=["cudacore", "tcgen05"])
 def test_conv_fused_shortcut_three_sources(cuda_dev, built_lib, impl):
     """ResBlock conv2 + 1x1 shortcut over the (h | skip) concat as extra K (Model.py:191-207)."""
