@@ -339,6 +339,11 @@ int its_candidate_scores(float* scores, const float* stats, const float* feats,
                          int32_t kind, void* stream);
 int its_argmax_first(int32_t* idx_out, float* val_out, const float* scores,
                      int32_t n, void* stream);
+/* The k best candidates under the same rule (score descending, first index on ties, NaN / -inf never rank):
+ * idx_out[r], val_out[r] for r < k; -1 / -inf past the number of eligible scores.  The reference keeps one
+ * winner (search_algorithm.py:79-81); north_star's "top-k/argmax" — used for keeping several pivots.       */
+int its_topk_first(int32_t* idx_out, float* val_out, const float* scores,
+                   int32_t n, int32_t k, void* stream);
 
 /* ------------------------------------------------------------------------
  * fp32-grade path (precision = "fp32").  The reference computes everything in

@@ -228,12 +228,10 @@ __device__ __forceinline__ void gn_tile_stats(float2* table, const float2* stats
   }
 }
 
-// y = acc * A + B, optional Swish (the formulation of gn_apply_stats_kernel: y * rcp(1 + 2^(-y log2 e)))
+// y = acc * A + B, optional Swish (gn_apply_stats_kernel's default formulation: h + h tanh(h), h = y / 2)
 __device__ __forceinline__ float gn_act(float acc, float A, float B, bool silu) {
   const float y = fmaf(acc, A, B);
-  float e;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * y));
-  return silu ? __fdividef(y, 1.0f + e) : y;
+  return silu ? silu_tanh_half(0.5f * y) : y;
 }
 
 // transposed-accumulator variant: one channel (scalar A, B), 64 pixels

@@ -20,6 +20,17 @@ bool pdl_enabled(int kind) {
   return g_pdl == 1 || (g_pdl == 2 && kind == 0) || (g_pdl == 3 && kind == 1);
 }
 
+// Swish formulation of the GroupNorm(+Swish) kernels: tanh (one special-function operation per element, default)
+// or exact (exp2 + reciprocal); ITS_SWISH=exact|tanh in the environment.
+bool swish_tanh_enabled() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("ITS_SWISH");
+    mode = (e != nullptr && e[0] == 'e') ? 0 : 1;
+  }
+  return mode == 1;
+}
+
 char* err_buf() {
   static thread_local char buf[512] = "";
   return buf;

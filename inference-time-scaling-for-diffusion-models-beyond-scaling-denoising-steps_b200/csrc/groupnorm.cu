@@ -264,7 +264,7 @@ struct GnStatArgs {
 };
 
 // FMT: 16-bit format of the sources at compile time — 0 = bf16, 1 = IEEE fp16, 2 = per source (run-time flags)
-template <int FMT>
+template <int FMT, bool TANH>
 __global__ void __launch_bounds__(GN_THREADS, 4) gn_apply_stats_kernel(const GnStatArgs a) {
   __shared__ float s_mean[64], s_rstd[64];
   const int tid = threadIdx.x;
@@ -339,8 +339,9 @@ __global__ void __launch_bounds__(GN_THREADS, 4) gn_apply_stats_kernel(const GnS
     const int g = (cv * 8 + i) / cg;
     scale[i] = s_rstd[g] * gam[i];
     shift[i] = bet[i] - s_mean[g] * scale[i];
-    nscale[i] = -1.4426950408889634f * scale[i];
-    nshift[i] = -1.4426950408889634f * shift[i];
+    // second affine map of the input: the exponent of the exact form, or half the normalised value for tanh
+    nscale[i] = (TANH ? 0.5f : -1.4426950408889634f) * scale[i];
+    nshift[i] = (TANH ? 0.5f : -1.4426950408889634f) * shift[i];
   }
   for (int pb = p0 + pl; pb < p1; pb += prow * U) {
     if (pb != p0 + pl) {
@@ -358,14 +359,16 @@ __global__ void __launch_bounds__(GN_THREADS, 4) gn_apply_stats_kernel(const GnS
         unpack8_fmt(raw[u], f, src_half);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const float v = fmaf(f[i], scale[i], shift[i]);
-          if (a.silu) {
+          if (a.silu && TANH) {
+            f[i] = silu_tanh_half(fmaf(f[i], nscale[i], nshift[i]));   // h + h tanh(h), h = v / 2
+          } else if (a.silu) {
             // v * rcp(1 + 2^(-v*log2e)); the exponent comes straight from the input (one FMA)
+            const float v = fmaf(f[i], scale[i], shift[i]);
             float e;
             asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fmaf(f[i], nscale[i], nshift[i])));
             f[i] = __fdividef(v, 1.0f + e);
           } else {
-            f[i] = v;
+            f[i] = fmaf(f[i], scale[i], shift[i]);
           }
         }
         *reinterpret_cast<bf16x8*>(a.out + ((long long)img * a.HW + p) * a.C + cv * 8) = a.out_fp16 ? pack8_half(f) : pack8(f);
@@ -471,13 +474,20 @@ extern "C" int its_group_norm_apply(void* out, const void* src0, int32_t C0, con
   a.chunks = (int)chunks;
   dim3 grid((unsigned)chunks, (unsigned)n_img);
   const int s1 = (C1 > 0) ? a.src1_fp16 : a.src0_fp16;
+  const bool th = swish_tanh_enabled();
+#define ITS_GN_APPLY(FMT_)                                                                                       \
+  do {                                                                                                          \
+    if (th) { ITS_LAUNCH((gn_apply_stats_kernel<FMT_, true>), dim3(grid), dim3(GN_THREADS), 0, as_stream(stream), a); } \
+    else { ITS_LAUNCH((gn_apply_stats_kernel<FMT_, false>), dim3(grid), dim3(GN_THREADS), 0, as_stream(stream), a); }   \
+  } while (0)
   if (a.src0_fp16 == 0 && s1 == 0) {
-    ITS_LAUNCH(gn_apply_stats_kernel<0>, dim3(grid), dim3(GN_THREADS), 0, as_stream(stream), a);
+    ITS_GN_APPLY(0);
   } else if (a.src0_fp16 == 1 && s1 == 1) {
-    ITS_LAUNCH(gn_apply_stats_kernel<1>, dim3(grid), dim3(GN_THREADS), 0, as_stream(stream), a);
+    ITS_GN_APPLY(1);
   } else {
-    ITS_LAUNCH(gn_apply_stats_kernel<2>, dim3(grid), dim3(GN_THREADS), 0, as_stream(stream), a);
+    ITS_GN_APPLY(2);
   }
+#undef ITS_GN_APPLY
   ITS_CHECK_LAUNCH();
   return ITS_OK;
 }

@@ -80,6 +80,18 @@ __device__ __forceinline__ float silu_f(float v) { return v / (1.0f + __expf(-v)
 // 2^-9 rounding in the 2e-2 sample tolerance once guidance amplifies it)
 __device__ __forceinline__ float silu_fast(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
 
+// Swish through ONE special-function operation: x * sigmoid(x) = h + h * tanh(h) with h = x / 2.  tanh.approx.f32
+// has a relative error of 2^-11, so the result carries an absolute error of at most |x| * 2.4e-4 — the size of
+// the IEEE fp16 rounding (2^-11 relative) the GroupNorm outputs receive when they are stored anyway.  The
+// GroupNorm-apply kernels are bound by the special-function unit (16 results per clock per SM against 128 FMAs):
+// exp2 + reciprocal is two operations per element, this is one (ITS_SWISH=exact restores the former).
+__device__ __forceinline__ float silu_tanh_half(float h) {     // h = x / 2
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+  return fmaf(h, t, h);
+}
+bool swish_tanh_enabled();
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -161,6 +161,54 @@ __global__ void __launch_bounds__(1024) argmax_first_kernel(int* __restrict__ id
   }
 }
 
+// Top-k selection, same ordering rule applied k times: rank r is the first index of the largest score that comes
+// after rank r-1 in the order (score descending, index ascending).  NaN and -inf never rank; ranks beyond the
+// number of eligible scores get index -1.  One block, warp-shuffle + shared-memory reduction per rank.
+__global__ void __launch_bounds__(1024) topk_first_kernel(int* __restrict__ idx_out, float* __restrict__ val_out,
+                                                          const float* __restrict__ scores, int n, int k) {
+  pdl_prologue();
+  __shared__ float s_v[32];
+  __shared__ int s_i[32];
+  __shared__ Best s_prev;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  Best prev = {INFINITY, -1};
+  for (int r = 0; r < k; ++r) {
+    Best b = {-INFINITY, -1};
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const float v = scores[i];
+      const bool after = r == 0 || v < prev.v || (v == prev.v && i > prev.i);
+      if (after && v > b.v) { b.v = v; b.i = i; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      Best t = {__shfl_xor_sync(0xffffffffu, b.v, o), __shfl_xor_sync(0xffffffffu, b.i, o)};
+      b = better(b, t);
+    }
+    if (lane == 0) { s_v[warp] = b.v; s_i[warp] = b.i; }
+    __syncthreads();
+    if (warp == 0) {
+      Best t = {-INFINITY, -1};
+      if (lane < (int)(blockDim.x >> 5)) { t.v = s_v[lane]; t.i = s_i[lane]; }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        Best u = {__shfl_xor_sync(0xffffffffu, t.v, o), __shfl_xor_sync(0xffffffffu, t.i, o)};
+        t = better(t, u);
+      }
+      if (lane == 0) {
+        idx_out[r] = t.i;
+        val_out[r] = t.v;
+        s_prev = t;
+      }
+    }
+    __syncthreads();
+    prev = s_prev;
+    if (prev.i < 0) {            // nothing left: the remaining ranks are empty
+      for (int q = r + 1 + threadIdx.x; q < k; q += blockDim.x) { idx_out[q] = -1; val_out[q] = -INFINITY; }
+      break;
+    }
+  }
+}
+
 }  // namespace its
 
 extern "C" int its_image_stats(float* stats, float* feats, const float* images, int32_t n_img,
@@ -190,6 +238,14 @@ extern "C" int its_argmax_first(int32_t* idx_out, float* val_out, const float* s
                                 void* stream) {
   ITS_REQUIRE(idx_out && val_out && scores && n > 0, "its_argmax_first: bad arguments");
   ITS_LAUNCH(its::argmax_first_kernel, dim3(1), dim3(1024), 0, its::as_stream(stream), idx_out, val_out, scores, n);
+  ITS_CHECK_LAUNCH();
+  return ITS_OK;
+}
+
+extern "C" int its_topk_first(int32_t* idx_out, float* val_out, const float* scores, int32_t n, int32_t k,
+                              void* stream) {
+  ITS_REQUIRE(idx_out && val_out && scores && n > 0 && k > 0, "its_topk_first: bad arguments");
+  ITS_LAUNCH(its::topk_first_kernel, dim3(1), dim3(1024), 0, its::as_stream(stream), idx_out, val_out, scores, n, k);
   ITS_CHECK_LAUNCH();
   return ITS_OK;
 }

@@ -98,7 +98,8 @@ class UNetPlan:
         self.fork_time_chain, self._side = False, None
         self.res_dtype = FP16 if (_os.environ.get("ITS_RESIDUAL_FP16", "0") == "1" and impl is None) else BF16
         self.gn_dtype = FP16 if (FP16_GN and impl != 1) else BF16
-        self.prefused, self.gn_fusion, self.n_gn_fused = {}, _os.environ.get("ITS_GN_FUSION", "1") != "0", 0
+        self.prefused, self.n_gn_fused = {}, 0
+        self.gn_fusion = {"0": "off", "1": "all"}.get(_os.environ.get("ITS_GN_FUSION", "1"), "auto")   # scratch plans: all
         return self
 
     # ------------------------------------------------------------ buffers --
@@ -171,6 +172,18 @@ class UNetPlan:
     # per clock, so narrow N tiles are operand-rate-bound, only the 256-wide one is tensor-bound.
     _T_KB = {256: 290.0, 192: 250.0, 128: 215.0, 64: 175.0}
     _T_SPLIT2 = 5000.0      # publish + re-read of the fp32 partial through L2, flag round trip
+
+    def _fusion_pays(self, Hm, Wm, cout, nkb) -> bool:
+        """Whether applying the consumer's GroupNorm in this layer's own epilogue beats the separate
+        its_group_norm_apply launch — from the layer shape only (never the batch: the two plans differ in
+        rounding, and a candidate's numbers must not depend on what it is batched with).  Measured on B200
+        (profiles/r02_gn_fusion_per_layer.txt): the second epilogue pass and the peer rendezvous cost 6-17 us
+        per launch unless a long K loop hides them behind the next tile's MMAs, so it pays only for 32x32 / 64x64
+        layers in transposed-accumulator mode (Cout = 128) with K >= 2304 (-2 .. -11 us per layer on configs A, C
+        and E); never on 16x16 maps (one round of 256-wide tiles: the chain is fully exposed), on 8x8 maps only
+        at 128 images per pass (a loss at 64, and the rule may not depend on the batch), break-even on 4x4."""
+        bw, bh, bb = self._box(Hm, Wm)
+        return bb == 1 and cout == 128 and Hm * Wm >= 1024 and nkb >= 36
 
     # N tiles that may split K inside the launch (ITS_SPLIT_BNS overrides, for measurements)
     _SPLIT_BNS = tuple(int(x) for x in _os.environ.get("ITS_SPLIT_BNS", "64").split(","))
@@ -263,8 +276,10 @@ class UNetPlan:
             d.res = None
         persistent = impl == 0 and self.L.its_conv_stats_parts(C.byref(d)) > 0
         bn, splits = 0, 1
-        want_fuse = (fuse_gn is not None and persistent and self.gn_fusion and want_stats and self.gn_dtype == FP16
-                     and len(phases) == 1 and out_scale == 1 and cout % fuse_gn[0].num_groups == 0)
+        want_fuse = (fuse_gn is not None and persistent and self.gn_fusion != "off" and want_stats
+                     and self.gn_dtype == FP16 and len(phases) == 1 and out_scale == 1
+                     and cout % fuse_gn[0].num_groups == 0
+                     and (self.gn_fusion == "all" or self._fusion_pays(Hm, Wm, cout, nkb_min)))
         if persistent and self.split_k:
             nkb_plan = nkb_min + (cout // 64 if can_fold else 0)
             bn, splits = 0, 0
@@ -621,10 +636,13 @@ class UNetPlan:
         self.stats_of, self.schedule, self.fold_residual = {}, 0, True
         self.ws_persist, self.sm_count, self.fused_attention = None, 148, True
         self.head_on_tensor_cores = True
-        # GroupNorm(+Swish) applied by the epilogue of the convolution that produces its input (ITS_GN_FUSION=0:
-        # every GroupNorm as its own its_group_norm_apply launch, the round-1 plan)
+        # GroupNorm(+Swish) applied by the epilogue of the convolution that produces its input.  ITS_GN_FUSION:
+        # auto (default) = where it was measured to pay (_fusion_pays), 1 = wherever the tiling allows it,
+        # 0 = never (every GroupNorm as its own its_group_norm_apply launch, the round-1 plan)
         self.prefused, self.n_gn_fused = {}, 0
-        self.gn_fusion = _os.environ.get("ITS_GN_FUSION", "1") != "0" and self.impl_forced is None
+        self.gn_fusion = {"0": "off", "1": "all"}.get(_os.environ.get("ITS_GN_FUSION", "auto"), "auto")
+        if self.impl_forced is not None:
+            self.gn_fusion = "off"
         # debugging switches (tests/parity triage): fall back to the simpler schedule of a stage
         self.schedule = int(_os.environ.get("ITS_SCHEDULE", "0"))
         self.fused_attention = _os.environ.get("ITS_FUSED_ATTENTION", "1") != "0"

@@ -171,8 +171,15 @@ def create_and_load_model(config: Dict[str, Any], device) -> nn.Module:
     # Raw feature maps in fp16 instead of bf16 (5x smaller error) need bounded activations:
     # `residual_fp16: auto` (default) turns it on for loaded checkpoints (trained weights) and leaves random
     # initialisations, whose state can grow past fp16's range, on bf16; true / false force it.
+    # `auto` never turns it on for schedules longer than the T = 1000 the checkpoints of this repository are trained
+    # on (an untrained or mismatched net drives |x_t| to ~2e5 at T = 2000, past fp16's 65504: the overflow would
+    # only surface as the sampler's "nan in tensor." assertion at the end of the trajectory).
     mode = config.get("residual_fp16", "auto")
-    model.residual_fp16 = bool(path) if mode == "auto" else bool(mode)
+    model.residual_fp16 = (bool(path) and int(config.get("T", 1000)) <= 1000) if mode == "auto" else bool(mode)
+    # `precision`: 16bit (default: tensor-core path, samples within 2e-2 of the fp32 reference) | fp32 (CUDA-core
+    # fp32 kernels, samples within 1e-4: the parity path)
+    model.precision = str(config.get("precision", "16bit")).lower()
+    print(f"its_b200: precision={model.precision} residual_fp16={model.residual_fp16} (residual_fp16: {mode})")
     return model.eval()
 
 
@@ -281,23 +288,27 @@ def run_search(sampler, config: Dict[str, Any], device, *, labels=None, seed: Op
     den = S.make_denoise_fn(sampler, labels, max_images=int(sc.get("max_images", 256)), seed=seed)
     dev = str(device)
     if algo == "random":
-        best, score = S.RandomSearch(n_candidates=int(sc.get("n_candidates", 4))).search(
-            shape, den, ver.score, device=dev, verbose=False, seed=seed)
+        search = S.RandomSearch(n_candidates=int(sc.get("n_candidates", 4)))
+        best, score = search.search(shape, den, ver.score, device=dev, verbose=False, seed=seed)
     else:
         x0 = S.philox_normal((1,) + shape, 0 if seed is None else seed, 0, S.TAG_X_T, torch.device(device))[0]
         if algo == "zero_order":
-            best, score, _ = S.ZeroOrderSearch(n_neighbors=int(sc.get("n_neighbors", 4)),
-                                               lambda_radius=float(sc.get("lambda_radius", 0.95)),
-                                               n_iterations=int(sc.get("n_iterations", 10))).search(
-                x0, den, ver.score, device=dev, verbose=False, seed=seed)
+            search = S.ZeroOrderSearch(n_neighbors=int(sc.get("n_neighbors", 4)),
+                                       lambda_radius=float(sc.get("lambda_radius", 0.95)),
+                                       n_iterations=int(sc.get("n_iterations", 10)))
+            best, score, _ = search.search(x0, den, ver.score, device=dev, verbose=False, seed=seed)
         elif algo == "path":
-            best, score, _ = S.PathSearch(n_paths=int(sc.get("n_paths", 4)),
-                                          injection_step=int(sc.get("injection_step", 400)),
-                                          noise_scale=float(sc.get("noise_scale", 0.1))).search(
-                x0, den, ver.score, device=dev, verbose=False, seed=seed)
+            search = S.PathSearch(n_paths=int(sc.get("n_paths", 4)), injection_step=int(sc.get("injection_step", 400)),
+                                  noise_scale=float(sc.get("noise_scale", 0.1)))
+            best, score, _ = search.search(x0, den, ver.score, device=dev, verbose=False, seed=seed)
         else:
             raise ValueError(f"search.algorithm {algo!r}: random | zero_order | path")
-    images = den(best) if best is not None else None
+    # the images of the winner: its own trajectory (the Philox stream of the candidate id it was scored under),
+    # so that the returned images are the ones that produced the returned score
+    images = None
+    if best is not None:
+        images = den.denoise_candidates(best.unsqueeze(0), max(0, int(getattr(search, "last_index", 0))),
+                                        seed=getattr(search, "last_seed", seed))[0]
     return best, score, images
 
 

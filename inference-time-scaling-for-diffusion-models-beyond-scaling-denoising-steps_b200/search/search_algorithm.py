@@ -53,6 +53,24 @@ class SamplerDenoiser:
         self.max_images = int(max_images)
         self.seed = seed
         self.step_noise = step_noise     # [T, B, C, H, W] shared by every candidate (parity runs)
+        self._calls = 0                  # callable mode: the i-th call of a search is global candidate i
+        self._fallback_seed: Optional[int] = None
+
+    def reset_calls(self) -> None:
+        """Callable mode numbers its candidates by call order; a search starts counting at zero."""
+        self._calls = 0
+
+    def step_seed(self, shared: Optional[int] = None) -> int:
+        """Seed of the per-step Philox noise: the denoiser's own, else the search's shared (broadcast) seed, else
+        one draw that then stays fixed for this denoiser (never a fresh one per call: a candidate's trajectory
+        must not depend on which call, rank or search round evaluates it)."""
+        if self.seed is not None:
+            return int(self.seed)
+        if shared is not None:
+            return int(shared)
+        if self._fallback_seed is None:
+            self._fallback_seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+        return self._fallback_seed
 
     def _labels_for(self, n_cand: int, kw_labels) -> Optional[torch.Tensor]:
         lab = kw_labels if kw_labels is not None else self.labels
@@ -61,19 +79,21 @@ class SamplerDenoiser:
         return lab.reshape(-1).repeat(n_cand)
 
     def __call__(self, noise: torch.Tensor, show_progress: bool = False, **kwargs) -> torch.Tensor:
-        return self.denoise_candidates(noise.unsqueeze(0), 0, labels=kwargs.get("labels"))[0]
+        # the reference draws fresh step noise for every candidate (Diffusion.py:96): candidate i of a serial
+        # search uses Philox stream i, exactly the stream population mode gives global candidate i
+        i = self._calls
+        self._calls += 1
+        return self.denoise_candidates(noise.unsqueeze(0), i, labels=kwargs.get("labels"))[0]
 
     def denoise_candidates(self, cands: torch.Tensor, first_cand: int, *, labels=None,
-                           t_start: Optional[int] = None) -> torch.Tensor:
+                           t_start: Optional[int] = None, seed: Optional[int] = None) -> torch.Tensor:
         """cands [n, B, C, H, W] -> images [n, B, C, H, W]; candidate i is global
         candidate first_cand + i (its Philox streams are keyed by that id)."""
         n, B = cands.shape[:2]
         guided = getattr(self.sampler, "guided", False)
         per_call = max(1, self.max_images // B)
         out = torch.empty_like(cands)
-        seed = self.seed
-        if seed is None:
-            seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+        seed = self.step_seed(seed)
         for i0 in range(0, n, per_call):
             i1 = min(n, i0 + per_call)
             x = cands[i0:i1].reshape((i1 - i0) * B, *cands.shape[2:])
@@ -173,12 +193,26 @@ def argmax_first(scores: torch.Tensor) -> Tuple[int, float]:
     return int(idx.item()), float(val.item())
 
 
+def topk_first(scores: torch.Tensor, k: int) -> Tuple[List[int], List[float]]:
+    """The k best (indices, values) under argmax_first's rule (strict '>', first index on ties, NaN never ranks);
+    indices are -1 past the number of eligible scores."""
+    _lib.require_cuda()
+    s = scores.detach().to(torch.float32).contiguous()
+    idx = torch.empty(k, dtype=torch.int32, device=s.device)
+    val = torch.empty(k, dtype=torch.float32, device=s.device)
+    with torch.cuda.device(s.device):
+        _lib.check(_lib.lib().its_topk_first(idx.data_ptr(), val.data_ptr(), s.data_ptr(), s.numel(), int(k),
+                                             _lib.stream_ptr(s.device)), "its_topk_first")
+    return idx.tolist(), val.tolist()
+
+
 def _score_population(cands_local: torch.Tensor, lo: int, n_total: int, denoise: SamplerDenoiser, ver,
-                      kwargs, t_start=None) -> torch.Tensor:
-    """Denoise + score this rank's block of candidates, return ALL n_total scores."""
+                      kwargs, t_start=None, seed=None) -> torch.Tensor:
+    """Denoise + score this rank's block of candidates, return ALL n_total scores.  `seed`: the search's
+    shared seed, used for the step noise when the denoiser has none of its own (same on every rank)."""
     B = cands_local.shape[1] if cands_local.numel() else 1
     if cands_local.shape[0] > 0:
-        imgs = denoise.denoise_candidates(cands_local, lo, labels=kwargs.get("labels"), t_start=t_start)
+        imgs = denoise.denoise_candidates(cands_local, lo, labels=kwargs.get("labels"), t_start=t_start, seed=seed)
         local = ver.score_candidates(imgs.reshape(-1, *imgs.shape[2:]), B)
     else:
         local = torch.empty(0, dtype=torch.float32, device=cands_local.device)
@@ -199,6 +233,8 @@ class RandomSearch:
         seed = kwargs.pop("seed", None)
         ver = _population_mode(denoise_fn, verifier_fn)
         n = self.n_candidates
+        if isinstance(denoise_fn, SamplerDenoiser):
+            denoise_fn.reset_calls()
         if ver is None:
             best_noise, best_score = None, float('-inf')
             for i in range(n):
@@ -213,6 +249,7 @@ class RandomSearch:
         dist, rank, world = _dist()
         dev = torch.device(device)
         seed = _shared_seed(seed, dev)
+        self.last_seed = seed
         lo, hi = _shard(n, rank, world)
         B = noise_shape[0]
         if cand_noise is not None:
@@ -221,7 +258,7 @@ class RandomSearch:
             local = philox_normal((hi - lo,) + tuple(noise_shape), seed, lo, TAG_X_T, dev) \
                 if hi > lo else torch.empty((0, *noise_shape), device=dev)
         with torch.no_grad():
-            scores = _score_population(local, lo, n, denoise_fn, ver, kwargs)
+            scores = _score_population(local, lo, n, denoise_fn, ver, kwargs, seed=seed)
         self.nfes += n
         self.last_scores = scores
         idx, val = argmax_first(scores)
@@ -265,9 +302,13 @@ class ZeroOrderSearch:
         history: Dict[str, Any] = {'scores': [], 'candidates_per_iter': []}
         K = self.n_neighbors
         radius = 1 - self.lambda_radius
+        self.last_index = -1                # global candidate id (round * K + neighbour) of the returned noise
+        if isinstance(denoise_fn, SamplerDenoiser):
+            denoise_fn.reset_calls()
         if ver is not None:
             dist, rank, world = _dist()
             seed = _shared_seed(seed, initial_noise.device)
+            self.last_seed = seed
         for it in range(self.n_iterations):
             if ver is None:
                 if perts is not None:
@@ -282,7 +323,7 @@ class ZeroOrderSearch:
                     score = verifier_fn(denoised, **kwargs)
                     it_scores.append(score)
                     if score > it_best:
-                        it_best, it_best_noise = score, nb.clone()
+                        it_best, it_best_noise, idx = score, nb.clone(), k
             else:
                 lo, hi = _shard(K, rank, world)
                 B = current.shape[0]
@@ -294,7 +335,7 @@ class ZeroOrderSearch:
                 else:
                     local = current.new_empty((0, *current.shape))
                 with torch.no_grad():
-                    scores = _score_population(local, lo + it * K, K, denoise_fn, ver, kwargs)
+                    scores = _score_population(local, lo + it * K, K, denoise_fn, ver, kwargs, seed=seed)
                 self.nfes += K
                 it_scores = [float(s) for s in scores.tolist()]
                 idx, it_best = argmax_first(scores)
@@ -312,6 +353,7 @@ class ZeroOrderSearch:
                 best_score = it_best
                 best_noise = it_best_noise.clone()
                 current = it_best_noise.clone()
+                self.last_index = it * K + idx
         return best_noise, best_score, history
 
     def reset_nfes(self):
@@ -344,6 +386,9 @@ class PathSearch:
         best_noise, best_score = initial_noise.clone(), float('-inf')
         history: Dict[str, Any] = {'scores': [], 'injection_points': []}
         P = self.n_paths
+        self.last_index = -1                # path index of the returned noise
+        if isinstance(denoise_fn, SamplerDenoiser):
+            denoise_fn.reset_calls()
         if ver is None:
             if restart:
                 raise ValueError("restart=True needs an its_b200 SamplerDenoiser (population mode)")
@@ -357,10 +402,11 @@ class PathSearch:
                 history['scores'].append(score)
                 history['injection_points'].append(self.injection_step)
                 if score > best_score:
-                    best_score, best_noise = score, perturbed.clone()
+                    best_score, best_noise, self.last_index = score, perturbed.clone(), p
             return best_noise, best_score, history
         dist, rank, world = _dist()
         seed = _shared_seed(seed, initial_noise.device)
+        self.last_seed = seed
         lo, hi = _shard(P, rank, world)
         B = initial_noise.shape[0]
         base = initial_noise
@@ -371,7 +417,7 @@ class PathSearch:
             T = smp.T
             if not (0 < self.injection_step < T):
                 raise ValueError("injection_step must lie in (0, T)")
-            base = _run_prefix(denoise_fn, initial_noise, self.injection_step, kwargs.get("labels"))
+            base = _run_prefix(denoise_fn, initial_noise, self.injection_step, kwargs.get("labels"), seed)
             t_start = self.injection_step - 1
 
         def perturbed(i0, i1):
@@ -383,13 +429,13 @@ class PathSearch:
                                  base=base.reshape(-1), scale=self.noise_scale)
 
         with torch.no_grad():
-            scores = _score_population(perturbed(lo, hi), lo, P, denoise_fn, ver, kwargs, t_start=t_start)
+            scores = _score_population(perturbed(lo, hi), lo, P, denoise_fn, ver, kwargs, t_start=t_start, seed=seed)
         self.nfes += P
         history['scores'] = [float(s) for s in scores.tolist()]
         history['injection_points'] = [self.injection_step] * P
         idx, val = argmax_first(scores)
         if idx >= 0:
-            best_score, best_noise = val, perturbed(idx, idx + 1)[0].clone()
+            best_score, best_noise, self.last_index = val, perturbed(idx, idx + 1)[0].clone(), idx
         return best_noise, best_score, history
 
     def reset_nfes(self):
@@ -436,12 +482,11 @@ class GradientBasedSearch:
         self.nfes = 0
 
 
-def _run_prefix(denoise: SamplerDenoiser, x_T: torch.Tensor, stop_step: int, labels) -> torch.Tensor:
+def _run_prefix(denoise: SamplerDenoiser, x_T: torch.Tensor, stop_step: int, labels, seed=None) -> torch.Tensor:
     """Run the pivot trajectory from T-1 down to `stop_step` inclusive as one device-resident segment
     of the sampler's step graph and return the un-clipped state that step `stop_step - 1` starts from."""
     smp = denoise.sampler
-    seed = denoise.seed if denoise.seed is not None else 0
-    kw = dict(seed=seed, cand_id0=0, t_stop=stop_step, clip=False)
+    kw = dict(seed=denoise.step_seed(seed), cand_id0=0, t_stop=stop_step, clip=False)
     if denoise.step_noise is not None:          # parity runs: the pivot's prefix uses the injected Gaussians too
         kw["noise"] = denoise.step_noise
     if getattr(smp, "guided", False):

@@ -398,7 +398,7 @@ def test_fused_group_norm_matches_the_two_launch_plan(cuda_dev, built_lib):
     outs, xin = {}, nhwc(x)
     for fused in (False, True):
         plan = UNetPlan.scratch(dev, B, 0)
-        plan.gn_fusion = fused
+        plan.gn_fusion = "all" if fused else "off"
         h1 = plan.conv([(xin, Cc, 0, 1, False)], [(taps_square(3), 0, 0, 0)], H, H, pack_conv_weight(w1).contiguous(),
                        Cc, fuse_gn=(gn, True), gn_only=True)
         a2 = plan.group_norm([h1], gn, True)
@@ -703,3 +703,18 @@ def test_argmax_first(cuda_dev, built_lib):
     s[[123, 60000]] = 9.0
     assert argmax_first(s) == (123, 9.0)
     assert argmax_first(torch.tensor([3.0], device=cuda_dev)) == (0, 3.0)
+
+
+def test_topk_first(cuda_dev, built_lib):
+    """its_topk_first: score descending, first index on ties, NaN / -inf never rank, -1 past the eligible ones."""
+    from its_b200.search.search_algorithm import argmax_first, topk_first
+    v = torch.tensor([0.5, float("nan"), 2.0, 2.0, -1.0, float("-inf"), 0.5, 2.0], device=cuda_dev)
+    idx, val = topk_first(v, 8)
+    assert idx == [2, 3, 7, 0, 6, 4, -1, -1]
+    assert val[:6] == [2.0, 2.0, 2.0, 0.5, 0.5, -1.0]
+    g = torch.Generator().manual_seed(3)
+    s = torch.randn(5000, generator=g).to(cuda_dev)
+    idx, val = topk_first(s, 17)
+    ref = torch.sort(s, descending=True, stable=True)
+    assert idx == ref.indices[:17].tolist() and val == ref.values[:17].tolist()
+    assert idx[0] == argmax_first(s)[0]

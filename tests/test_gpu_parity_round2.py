@@ -275,3 +275,68 @@ def test_fp32_mode_cross_checks_the_tensor_core_plan_on_device(cuda_dev):
     slow = net(x, t)
     print("16-bit plan vs fp32 plan, config A, 16 images: rel err %.2e rms %.2e" % (rel_err(fast, slow), rms_err(fast, slow)))
     assert rms_err(fast, slow) < 1e-2 and rel_err(fast, slow) < 3e-2
+
+
+# ------------------------------------------------------------------------------ driver / search housekeeping --
+def test_fp16_residual_stream_overflow_raises_nan_in_tensor(cuda_dev):
+    """The opt-in fp16 residual stream cannot hold a state beyond 65504: the overflow must surface as the sampler's
+    own AssertionError("nan in tensor."), never as silently wrong samples; the default bf16 stream runs the same
+    input through."""
+    from its_b200.Diffusion import GaussianDiffusionSampler
+    cfg = cases.SAMPLER_CASES["u_small_T20"]
+    x_T, noise, _ = cases.sampler_inputs(cfg)
+    big = (x_T * 3e5).to(cuda_dev)
+    net, _ = build_shell(cfg, cuda_dev)
+    smp = GaussianDiffusionSampler(net, cfg["beta_1"], cfg["beta_T"], cfg["T"]).to(cuda_dev)
+    smp.print_steps = False
+    out = smp(big, noise=noise.to(cuda_dev))
+    assert torch.isfinite(out).all()
+    net.residual_fp16 = True
+    net.invalidate_plans()
+    with pytest.raises(AssertionError, match="nan in tensor"):
+        smp(big, noise=noise.to(cuda_dev))
+
+
+def test_driver_residual_fp16_auto_policy(tmp_path, cuda_dev):
+    """`residual_fp16: auto` turns the fp16 residual stream on for a loaded checkpoint at T <= 1000 only; T = 2000
+    (an untrained or mismatched net reaches |x_t| ~ 2e5 there) keeps bf16 unless the config forces it."""
+    from its_b200 import inference as I
+    cfg = dict(cases.SAMPLER_CASES["u_small_T20"])
+    net, sd = build_shell(cfg, None)
+    ck = tmp_path / "ckpt.pt"
+    torch.save(sd, ck)
+    base = dict(T=cfg["T"], channel=cfg["ch"], channel_mult=cfg["ch_mult"], attn=cfg["attn"],
+                num_res_blocks=cfg["num_res_blocks"], dropout=cfg["dropout"], img_size=cfg["img"])
+    for T, mode, path, want in ((1000, "auto", str(ck), True), (2000, "auto", str(ck), False),
+                                (2000, True, str(ck), True), (1000, False, str(ck), False), (1000, "auto", None, False)):
+        m = I.create_and_load_model(dict(base, T=T, residual_fp16=mode, checkpoint_path=path), cuda_dev)
+        assert bool(m.residual_fp16) is want, (T, mode, path)
+        assert m.precision == "16bit"
+    assert I.create_and_load_model(dict(base, precision="fp32", checkpoint_path=None), cuda_dev).precision == "fp32"
+
+
+def test_callable_mode_candidates_use_their_own_noise_streams(cuda_dev):
+    """Serial (callable) mode: the i-th candidate of a search runs on Philox stream i — fresh step noise per
+    candidate like the reference's randn_like (Diffusion.py:96) — i.e. exactly the trajectory population mode
+    gives global candidate i, so both modes return the same scores and the same winner."""
+    cfg = cases.SEARCH_CASES["u_search"]
+    net, _ = build_shell(cfg, cuda_dev)
+    smp = _sampler(cfg, net, cuda_dev)
+    from its_b200.search import search_algorithm as S
+    from its_b200.search import verifier as V
+    ver = V.OracleVerifier()
+    den = S.make_denoise_fn(smp, None, seed=11)
+    shape = tuple(cfg["noise_shape"])
+    cands = cases._randn(77, (5,) + shape).to(cuda_dev)
+    rs = S.RandomSearch(n_candidates=5)
+    n1, s1 = rs.search(shape, den, ver.score, device="cuda", verbose=False, candidate_noise=cands)
+    pop = [float(x) for x in rs.last_scores.tolist()]
+    seen = []
+    rs2 = S.RandomSearch(n_candidates=5)
+    n2, s2 = rs2.search(shape, den, lambda im, **kw: seen.append(ver.score(im)) or seen[-1], device="cuda",
+                        verbose=False, candidate_noise=cands)
+    assert seen == pop and s2 == s1 and torch.equal(n1, n2)
+    assert len(set(pop)) == 5                      # different streams: no two candidates share a trajectory
+    # the images of the winner are the ones that produced its score
+    img = den.denoise_candidates(n1.unsqueeze(0), rs.last_index)[0]
+    assert ver.score(img) == s1
