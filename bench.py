@@ -359,6 +359,8 @@ def run_ours(args):
     n_net = 2 * n_local if wl["cond"] else n_local
     plan = net.plan(n_net, img, img, n_img_in=n_local, uniform_t=True)
     roof = profile_tapgemm(plan, dev, pk)
+    if roof["launches_per_unet_pass"] == 0:          # the fp32 parity path launches no tcgen05 kernel
+        roof.update(achieved=0.0, frac=0.0, kernel="f32_conv2d_kernel (CUDA cores; --precision fp32 is the parity path)")
     roof["step_share"] = roof.pop("sum_ms") * T / ms_per_step if ms_per_step else None
     roof["model_flops_frac_of_sustained"] = (value / world) * plan.flops / n_local * T / (pk["sustained"] * 1e12)
     if args.workload == "A" and n_local == 64:
@@ -366,7 +368,7 @@ def run_ours(args):
     hbm = profile_hbm_kernels(plan, smp, dev, pk, n_local, img, wl)
     # BASELINE.json configs[2] and configs[4] on the same record: one bounded search each (N = 1 default run only)
     extra = None
-    if world == 1 and args.workload == "A" and not args.no_extra_workloads:
+    if world == 1 and args.workload == "A" and not args.no_extra_workloads and PRECISION == "16bit":
         extra = {k: run_extra_workload(k, dev, pk) for k in ("C", "E")}
 
     line = None
@@ -381,7 +383,8 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16/fp16 operands, fp32 accumulate", "data": "synthetic", "config": workload_config(args, world),
+            "dtype": "f32" if PRECISION == "fp32" else "bf16/fp16 operands, fp32 accumulate", "data": "synthetic",
+            "config": workload_config(args, world),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": gpu_launches, "roofline": roof, "roofline_hbm_kernels": hbm, "cpu_baseline": cpu,
             "clocks": clocks.summary(),
@@ -394,6 +397,9 @@ def run_ours(args):
         dist.barrier()
         dist.destroy_process_group()
     return line
+
+
+PRECISION = "16bit"     # --precision: "16bit" (tensor-core path, the headline) or "fp32" (CUDA-core parity path)
 
 
 def build_workload(key, dev):
@@ -412,6 +418,7 @@ def build_workload(key, dev):
         net = UNet(**dict(CFG_A, T=T, attn=wl["attn"])).to(dev).eval()
         smp = GaussianDiffusionSampler(net, BETA_1, BETA_T, T).to(dev)
     smp.print_steps = False
+    net.precision = PRECISION
     return net, smp, labels
 
 
@@ -566,7 +573,11 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra-workloads", action="store_true",
                     help="skip the one-search measurements of workloads C and E appended to the default line")
+    ap.add_argument("--precision", default="16bit", choices=["16bit", "fp32"],
+                    help="16bit = tensor-core path (default, the headline number); fp32 = CUDA-core parity path")
     args = ap.parse_args()
+    global PRECISION
+    PRECISION = args.precision
     if args.candidates is None:
         args.candidates = WORKLOADS[args.workload]["candidates"]
     if args.impl == "reference":
