@@ -104,6 +104,10 @@ class SamplerBase(nn.Module):
         net = self._unet()
         if net.head.weight.device != x_T.device:
             raise RuntimeError(f"x_T lives on {x_T.device} but the UNet on {net.head.weight.device}")
+        if self.guided:
+            if getattr(net, "is_conditional", False) and self.T > net.time_embedding.timembedding[0].num_embeddings:
+                raise IndexError("index out of range in self")     # the net's time table is shorter than the schedule
+            net.check_indices(None, labels)
         B, Cc, H, W = x_T.shape
         n_net = 2 * B if self.guided else B
         plan = net.plan(n_net, H, W, n_img_in=B, uniform_t=True, impl=getattr(net, "impl", None))

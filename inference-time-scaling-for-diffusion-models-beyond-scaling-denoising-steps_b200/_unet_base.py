@@ -56,6 +56,20 @@ class PlannedUNet(nn.Module):
             self._plans[key] = p
         return p
 
+    def check_indices(self, t: Optional[torch.Tensor], labels: Optional[torch.Tensor]) -> None:
+        """nn.Embedding raises IndexError on an index outside its table (the conditional net's time table
+        `[T, ch]`, ModelCondition.py:38, and label table `[num_labels + 1, ch]`, :52-54): same error here, instead
+        of reading a neighbouring row.  One host synchronisation per call (the samplers call it once per
+        trajectory, not per step)."""
+        if not self.is_conditional:
+            return
+        te = self.time_embedding.timembedding[0]
+        if t is not None and t.numel() and bool(((t < 0) | (t >= te.num_embeddings)).any()):
+            raise IndexError("index out of range in self")
+        ce = self.cond_embedding.condEmbedding[0]
+        if labels is not None and labels.numel() and bool(((labels < 0) | (labels >= ce.num_embeddings)).any()):
+            raise IndexError("index out of range in self")
+
     def _run(self, x: torch.Tensor, t: torch.Tensor, labels: Optional[torch.Tensor]) -> torch.Tensor:
         if x.device.type != "cuda":
             raise RuntimeError("its_b200 UNet runs on CUDA only (no CPU fallback)")
@@ -64,6 +78,7 @@ class PlannedUNet(nn.Module):
         if self.head.weight.device != x.device:
             raise RuntimeError(f"x lives on {x.device} but the UNet on {self.head.weight.device}")
         B, _, H, W = x.shape
+        self.check_indices(t, labels)
         with torch.cuda.device(x.device):     # launches go to this device's current stream
             p = self.plan(B, H, W, impl=getattr(self, "impl", None))
             with torch.no_grad():

@@ -25,9 +25,10 @@ __global__ void embed_rows_kernel(float* __restrict__ out, const float* __restri
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_rows * dim) return;
   const int b = i / dim, j = i - b * dim;
-  long long r = (idx != nullptr) ? idx[b] : (long long)(*t_dev);
-  r = r < 0 ? 0 : (r >= n_table_rows ? n_table_rows - 1 : r);  // never read outside the table
-  out[i] = table[r * (long long)dim + j];
+  const long long r = (idx != nullptr) ? idx[b] : (long long)(*t_dev);
+  // nn.Embedding raises on an index outside the table (the host shells check it); the kernel never reads outside
+  // the table and marks such a row with NaN, which the sampler's "nan in tensor." assertion reports
+  out[i] = (r < 0 || r >= n_table_rows) ? __int_as_float(0x7fc00000) : table[r * (long long)dim + j];
 }
 
 // y[b, n] = sum_k act(x[b,k]) W[n,k] + bias[n]; one warp per (b, n): lanes stride

@@ -340,3 +340,20 @@ def test_callable_mode_candidates_use_their_own_noise_streams(cuda_dev):
     # the images of the winner are the ones that produced its score
     img = den.denoise_candidates(n1.unsqueeze(0), rs.last_index)[0]
     assert ver.score(img) == s1
+
+
+def test_out_of_range_labels_and_steps_raise_like_nn_embedding(cuda_dev):
+    """ModelCondition's tables are nn.Embedding: an index outside them raises IndexError in the reference; the shell
+    raises the same error instead of reading a neighbouring row (and the kernel itself marks such a row NaN)."""
+    cfg = cases.SAMPLER_CASES["c_small_T20"]
+    net, _ = build_shell(cfg, cuda_dev)
+    x, t, labels = cases.forward_inputs(cfg)
+    x, t, labels = x.to(cuda_dev), t.to(cuda_dev), labels.to(cuda_dev)
+    net(x, t, labels)
+    with pytest.raises(IndexError):
+        net(x, t, labels + cfg["num_labels"] + 1)
+    with pytest.raises(IndexError):
+        net(x, t + cfg["T"], labels)
+    smp = _sampler(cfg, net, cuda_dev)
+    with pytest.raises(IndexError):
+        smp(x, torch.full_like(labels, cfg["num_labels"] + 3))
