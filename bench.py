@@ -464,8 +464,8 @@ def run_extra_workload(key, dev, pk):
 
 def ncu_traffic(family):
     """DRAM bytes (read + write) of one UNet pass of this kernel family, from the committed ncu capture of
-    this workload (profiles/r01_traffic_configA_b64.json, written by scripts/summarize_launches.py)."""
-    path = os.path.join(ROOT, "profiles", "r01_traffic_configA_b64.json")
+    this workload (profiles/r02_traffic_configA_b64.json, written by scripts/summarize_launches.py)."""
+    path = os.path.join(ROOT, "profiles", "r02_traffic_configA_b64.json")
     try:
         rec = json.load(open(path))
         fam = rec["families"][family]

@@ -84,21 +84,30 @@ __global__ void __launch_bounds__(256) f32_conv2d_kernel(const F32ConvArgs a) {
         if (!okx) continue;
         const float* w = a.Wt + ((long long)(ky * a.k + kx) * Cin) * a.CoutP + nq * 4;
         const long long ipix = (b * a.Hin + iy) * a.Win + ix;
-        const float* p0 = a.in0 + ipix * a.C0;
-        for (int c = 0; c < a.C0; ++c) {
-          const float v = __ldg(p0 + c);
-          const float4 w4 = __ldg(reinterpret_cast<const float4*>(w + (long long)c * a.CoutP));
-          acc0 = fmaf(v, w4.x, acc0); acc1 = fmaf(v, w4.y, acc1); acc2 = fmaf(v, w4.z, acc2); acc3 = fmaf(v, w4.w, acc3);
-        }
-        if (a.C1 > 0) {
-          const float* p1 = a.in1 + ipix * a.C1;
-          const float* w1 = w + (long long)a.C0 * a.CoutP;
-          for (int c = 0; c < a.C1; ++c) {
-            const float v = __ldg(p1 + c);
-            const float4 w4 = __ldg(reinterpret_cast<const float4*>(w1 + (long long)c * a.CoutP));
+        // channels in ascending order, one FMA chain per output channel (the summation order is the same
+        // whether a source is read four channels at a time or one by one)
+        auto run = [&](const float* src, int C, const float* wsrc) {
+          int c = 0;
+          if ((C & 3) == 0) {
+            for (; c < C; c += 4) {
+              const float4 v4 = __ldg(reinterpret_cast<const float4*>(src + c));
+              const float vv[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float4 w4 = __ldg(reinterpret_cast<const float4*>(wsrc + (long long)(c + j) * a.CoutP));
+                acc0 = fmaf(vv[j], w4.x, acc0); acc1 = fmaf(vv[j], w4.y, acc1);
+                acc2 = fmaf(vv[j], w4.z, acc2); acc3 = fmaf(vv[j], w4.w, acc3);
+              }
+            }
+          }
+          for (; c < C; ++c) {
+            const float v = __ldg(src + c);
+            const float4 w4 = __ldg(reinterpret_cast<const float4*>(wsrc + (long long)c * a.CoutP));
             acc0 = fmaf(v, w4.x, acc0); acc1 = fmaf(v, w4.y, acc1); acc2 = fmaf(v, w4.z, acc2); acc3 = fmaf(v, w4.w, acc3);
           }
-        }
+        };
+        run(a.in0 + ipix * a.C0, a.C0, w);
+        if (a.C1 > 0) run(a.in1 + ipix * a.C1, a.C1, w + (long long)a.C0 * a.CoutP);
       }
     }
     const float acc[4] = {acc0, acc1, acc2, acc3};
