@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libits_b200.so")
+# ITS_LIB: another build of the same ABI (A/B measurements of a kernel change on one box)
+LIB_PATH = os.environ.get("ITS_LIB") or os.path.join(_HERE, "libits_b200.so")
 
 MAX_SRC, MAX_TAPS, MAX_PHASES = 3, 36, 4
 
