@@ -15,9 +15,14 @@ static int g_pdl = -1;   // -1: read ITS_PDL from the environment on first use
 bool pdl_enabled(int kind) {
   if (g_pdl < 0) {
     const char* e = getenv("ITS_PDL");
-    g_pdl = (e != nullptr && e[0] >= '0' && e[0] <= '3') ? (e[0] - '0') : 3;
+    g_pdl = (e != nullptr && e[0] >= '0' && e[0] <= '4') ? (e[0] - '0') : 3;
   }
-  return g_pdl == 1 || (g_pdl == 2 && kind == 0) || (g_pdl == 3 && kind == 1);
+  // 4 (experiment, round 2): tap-GEMMs and GroupNorm-apply, the latter WITHOUT an early trigger of its own
+  // dependents: 1 942 us per config-A pass against 1 757 for mode 3 (the GEMM behind the GroupNorm loses its
+  // early launch, and an early-launched GroupNorm grid is itself no faster) — every combination that puts the
+  // attribute on the GroupNorm launches loses (re-measured this round: 3 -> 1 757, 1 -> 1 870, 0 -> 1 884, 2 -> 1 948)
+  if (g_pdl == 4) return kind == 1 || kind == 2;
+  return g_pdl == 1 || (g_pdl == 2 && kind != 1) || (g_pdl == 3 && kind == 1);
 }
 
 // Swish formulation of the GroupNorm(+Swish) kernels: tanh (one special-function operation per element, default)
@@ -142,7 +147,7 @@ extern "C" int its_abi_sizeof(int which) {
                                                               : (int)sizeof(its_phase_t);
 }
 extern "C" int its_set_pdl(int32_t enabled) {
-  its::g_pdl = (enabled >= 0 && enabled <= 3) ? enabled : 3;
+  its::g_pdl = (enabled >= 0 && enabled <= 4) ? enabled : 3;
   return ITS_OK;
 }
 

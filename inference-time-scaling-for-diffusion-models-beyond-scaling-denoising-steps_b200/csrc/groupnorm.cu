@@ -261,6 +261,7 @@ struct GnStatArgs {
   int C0, C1, C, HW, groups, parts0, parts1, silu, chunks, out_fp16;
   int src0_fp16, src1_fp16;     // 16-bit format of the sources (raw feature maps: bf16 unless the fp16 residual stream is on)
   float eps;
+  int late_trigger;             // 1: do not release the dependent launch at kernel start (ITS_PDL=4 experiment)
 };
 
 // FMT: 16-bit format of the sources at compile time — 0 = bf16, 1 = IEEE fp16, 2 = per source (run-time flags)
@@ -283,7 +284,7 @@ __global__ void __launch_bounds__(GN_THREADS, 4) gn_apply_stats_kernel(const GnS
   const int spitch = from0 ? a.C0 : a.C1;
   const bool src_half = FMT == 2 ? ((from0 ? a.src0_fp16 : a.src1_fp16) != 0) : (FMT == 1);
   constexpr int U = 4;                   // independent 16-byte loads in flight per thread
-  pdl_prologue();
+  if (a.late_trigger) asm volatile("griddepcontrol.wait;" ::: "memory"); else pdl_prologue();
   // first batch of activations and the affine parameters are requested before the
   // statistics chain below, so the two global round trips overlap
   bf16x8 raw[U];
@@ -475,10 +476,11 @@ extern "C" int its_group_norm_apply(void* out, const void* src0, int32_t C0, con
   dim3 grid((unsigned)chunks, (unsigned)n_img);
   const int s1 = (C1 > 0) ? a.src1_fp16 : a.src0_fp16;
   const bool th = swish_tanh_enabled();
+  a.late_trigger = pdl_enabled(2) && !pdl_enabled(0);
 #define ITS_GN_APPLY(FMT_)                                                                                       \
   do {                                                                                                          \
-    if (th) { ITS_LAUNCH((gn_apply_stats_kernel<FMT_, true>), dim3(grid), dim3(GN_THREADS), 0, as_stream(stream), a); } \
-    else { ITS_LAUNCH((gn_apply_stats_kernel<FMT_, false>), dim3(grid), dim3(GN_THREADS), 0, as_stream(stream), a); }   \
+    if (th) { ITS_LAUNCH_KIND(2, (gn_apply_stats_kernel<FMT_, true>), dim3(grid), dim3(GN_THREADS), 0, as_stream(stream), a); } \
+    else { ITS_LAUNCH_KIND(2, (gn_apply_stats_kernel<FMT_, false>), dim3(grid), dim3(GN_THREADS), 0, as_stream(stream), a); }   \
   } while (0)
   if (a.src0_fp16 == 0 && s1 == 0) {
     ITS_GN_APPLY(0);

@@ -53,11 +53,26 @@ struct PerDeviceBytes {
 // consecutive launches on a stream overlap their launch latency / set-up with the tail of
 // the predecessor — when the launch carries the attribute (its_set_pdl / ITS_PDL; by default only the
 // tap-GEMM launches do, see the measurements in ddpm_step.cu).
-bool pdl_enabled(int kind = 0);   // kind: 0 = small kernel, 1 = tap-GEMM
+bool pdl_enabled(int kind = 0);   // kind: 0 = small kernel, 1 = tap-GEMM, 2 = GroupNorm-apply
 __device__ __forceinline__ void pdl_prologue() {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   asm volatile("griddepcontrol.wait;" ::: "memory");
 }
+
+#define ITS_LAUNCH_KIND(kind_, kernel_, grid_, block_, smem_, stream_, ...)                      \
+  do {                                                                                         \
+    cudaLaunchConfig_t _cfg = {};                                                              \
+    _cfg.gridDim = (grid_);                                                                    \
+    _cfg.blockDim = (block_);                                                                  \
+    _cfg.dynamicSmemBytes = (smem_);                                                           \
+    _cfg.stream = (stream_);                                                                   \
+    cudaLaunchAttribute _at[1];                                                                \
+    _at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                            \
+    _at[0].val.programmaticStreamSerializationAllowed = 1;                                     \
+    _cfg.attrs = _at;                                                                          \
+    _cfg.numAttrs = ::its::pdl_enabled(kind_) ? 1 : 0;                                         \
+    ITS_CHECK_CUDA(cudaLaunchKernelEx(&_cfg, kernel_, __VA_ARGS__));                           \
+  } while (0)
 
 #define ITS_LAUNCH(kernel_, grid_, block_, smem_, stream_, ...)                                   \
   do {                                                                                         \
