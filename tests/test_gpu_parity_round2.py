@@ -262,6 +262,26 @@ def test_fp32_mode_full_length_trajectory_no_excused_pixels(cuda_dev):
     assert d.max().item() <= SAMPLE_TOL
 
 
+@pytest.mark.parametrize("name,fixture", [("c_C_T1000", "smp_c_C_T1000"), ("u_E_T2000", "smp_u_E_T2000")])
+def test_fp32_mode_first_segment_of_configs_C_and_E(cuda_dev, name, fixture):
+    """fp32 mode on the guided net (CFG w = 1.8, config C's real width) and on the 64x64 net (config E): the first
+    segment of the full-length fixtures (steps T-1 .. first checkpoint: 100 resp. 200 steps — the CUDA-core path is
+    slow) reproduces the reference's un-clipped state to 1e-5 relative."""
+    cfg = cases.LONG_CASES[name]
+    g = golden(fixture)
+    net, _ = build_shell(cfg, cuda_dev)
+    net.precision = "fp32"
+    smp = _sampler(cfg, net, cuda_dev)
+    x_T, noise, labels = cases.sampler_inputs(cfg)
+    stop = cfg["keep_at"][0]
+    kw = dict(noise=noise.to(cuda_dev), t_start=cfg["T"] - 1, t_stop=stop, clip=False)
+    x = smp(x_T.to(cuda_dev), labels.to(cuda_dev), **kw) if labels is not None else smp(x_T.to(cuda_dev), **kw)
+    ref = torch.from_numpy(g[f"x_after_{stop}"]).to(cuda_dev)
+    print("fp32 mode %s after step %d: |x|max %.3e rel err %.2e max abs %.2e" % (name, stop, ref.abs().max().item(),
+                                                                              rel_err(x, ref), (x - ref).abs().max().item()))
+    assert rel_err(x, ref) < 1e-5
+
+
 def test_fp32_mode_cross_checks_the_tensor_core_plan_on_device(cuda_dev):
     """The two plans evaluate the same shell on the same inputs: the 16-bit tcgen05 plan stays within its error
     budget of the fp32 plan at config A's real width and a 64-image batch (no CPU fixture involved)."""
